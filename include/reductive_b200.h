@@ -1,0 +1,165 @@
+/*
+ * reductive_b200.h — C ABI of the B200-native product-quantization hot path.
+ *
+ * This is the drop-in boundary: every entry point is what reductive's FFI for this path would bind.
+ * Each declaration cites the reference interface it replaces (paths relative to /root/reference).
+ * Plain pointers and sizes only; no torch / ndarray types cross this boundary.
+ *
+ * Conventions
+ *   - Strides are in ELEMENTS (like ndarray), may be any non-zero value for inputs; views with
+ *     col_stride != 1 are packed on the device before the kernels run.
+ *   - `mem_kind` says where the data pointers of that call live (RB_MEM_HOST: ordinary or pinned host
+ *     memory, copied in chunks overlapped with the kernels; RB_MEM_DEVICE: device memory of the
+ *     CURRENT CUDA device, no copies).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device-memory calls
+ *     are asynchronous on that stream; host-memory calls return after the result is in host memory.
+ *   - One process drives one GPU (the current device); a handle belongs to the device that was
+ *     current when it was created.  Handles are immutable after creation: concurrent calls on one
+ *     handle from several threads / streams are legal (Pq is Sync in the reference, pq.rs:28).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     RB_ERR_NO_DEVICE / RB_ERR_CUDA.
+ *   - Codes are little-endian unsigned integers of `code_width` bytes (1, 2, 4 or 8) — the reference's
+ *     generic index type I (traits.rs:77-80).
+ */
+#ifndef REDUCTIVE_B200_H
+#define REDUCTIVE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+/* Status codes.  1..6 mirror ReductiveError (src/error.rs:6-41); 16.. are the reference's panics
+ * (assert sites: primitives.rs:25-34,74-87,123-135,159-167; pq.rs:39-55; kmeans.rs:61-71,269-277),
+ * which a Rust shim re-asserts before calling so that panic behaviour is preserved. */
+typedef enum rb_status {
+    RB_OK = 0,
+    RB_ERR_N_ATTEMPTS = 1,            /* ReductiveError::IncorrectNAttempts            error.rs:9  */
+    RB_ERR_N_ITERATIONS = 2,          /* ReductiveError::IncorrectNIterations          error.rs:12 */
+    RB_ERR_N_SUBQUANTIZER_BITS = 3,   /* ReductiveError::IncorrectNSubquantizerBits    error.rs:18 */
+    RB_ERR_NUMBER_SUBQUANTIZERS = 4,  /* ReductiveError::IncorrectNumberSubquantizers  error.rs:25 */
+    RB_ERR_N_SUBQUANTIZERS_RANGE = 5, /* ReductiveError::NSubquantizersOutsideRange    error.rs:35 */
+    RB_ERR_CONSTRUCT_RNG = 6,         /* ReductiveError::ConstructRng                  error.rs:40 */
+    RB_ERR_SHAPE = 16,                /* shape / length mismatch (reference: assert! panic)        */
+    RB_ERR_CODE_TYPE = 17,            /* k-1 does not fit the code type (primitives.rs:31-34)      */
+    RB_ERR_CODE_RANGE = 18,           /* code >= k in reconstruct (reference: ndarray index panic) */
+    RB_ERR_INVALID = 19,              /* NULL pointer / bad enum                                   */
+    RB_ERR_K_MEANS_K = 20,            /* k == 0 or k >= n instances (kmeans.rs:61-67)              */
+    RB_ERR_CUDA = 32,                 /* a CUDA runtime call or kernel failed                      */
+    RB_ERR_NO_DEVICE = 33,            /* no CUDA device visible                                    */
+    RB_ERR_UNSUPPORTED = 34           /* shape outside what the kernels cover (message says what)  */
+} rb_status;
+
+typedef enum rb_mem_kind { RB_MEM_HOST = 0, RB_MEM_DEVICE = 1 } rb_mem_kind;
+
+/* Which encode kernel quantize_batch / k-means assignment uses.  Both give bit-identical codes. */
+typedef enum rb_encode_algo {
+    RB_ENCODE_AUTO = 0,   /* tensor path when the shape allows it, otherwise exact SIMT */
+    RB_ENCODE_EXACT = 1,  /* FP32 SIMT kernel evaluating the reference's FMA chain directly */
+    RB_ENCODE_TENSOR = 2  /* tcgen05 candidate pass + exact recheck of near-ties (k <= 256, k % 16 == 0) */
+} rb_encode_algo;
+
+/* Opaque product quantizer: reference `Pq<f32>` (src/pq/pq.rs:29-32) resident on one GPU. */
+typedef struct rb_pq rb_pq;
+
+/* Thread-local description of the last non-OK status returned on this thread. */
+const char *rb_last_error_message(void);
+int rb_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t rb_kernel_launch_count(void);
+/* Process-wide default for RB_ENCODE_AUTO resolution (tests force each path). */
+rb_status rb_set_encode_algo(int algo);
+
+/* ---- Pq construction and accessors ----------------------------------------------------------- */
+
+/* Pq::new(projection, quantizers)  pq.rs:38-61.  quantizers: HOST [M,k,dsub] contiguous;
+ * projection: HOST [d,d] row-major (d = M*dsub) or NULL.  RB_ERR_SHAPE when any extent is 0. */
+rb_status rb_pq_create(const float *quantizers, size_t n_subquantizers, size_t n_centroids,
+                       size_t subquantizer_dim, const float *projection_or_null, rb_pq **out);
+void rb_pq_destroy(rb_pq *pq);
+size_t rb_pq_quantized_len(const rb_pq *pq);         /* QuantizeVector::quantized_len     pq.rs:300 */
+size_t rb_pq_reconstructed_len(const rb_pq *pq);     /* Reconstruct::reconstructed_len    pq.rs:345 */
+size_t rb_pq_n_quantizer_centroids(const rb_pq *pq); /* Pq::n_quantizer_centroids         pq.rs:103 */
+int rb_pq_has_projection(const rb_pq *pq);           /* Pq::projection().is_some()        pq.rs:108 */
+rb_status rb_pq_subquantizers(const rb_pq *pq, float *out_host);  /* Pq::subquantizers pq.rs:191 */
+rb_status rb_pq_projection(const rb_pq *pq, float *out_host);     /* Pq::projection    pq.rs:108 */
+
+/* ---- QuantizeVector (src/pq/traits.rs:75-99; impl pq.rs:252-303) ------------------------------ */
+
+/* quantize_batch_into  pq.rs:268-283 -> primitives.rs:64-104.  x [n, d] f32, codes [n, M].
+ * No check that k-1 fits code_width (the reference's batch path truncates, primitives.rs:100). */
+rb_status rb_pq_quantize_batch(const rb_pq *pq, const float *x, size_t n, ptrdiff_t x_row_stride,
+                               ptrdiff_t x_col_stride, void *codes, int code_width,
+                               ptrdiff_t code_row_stride, ptrdiff_t code_col_stride,
+                               int mem_kind, void *stream);
+/* quantize_vector  pq.rs:285-298 -> primitives.rs:14-49 (mat-vec arithmetic, differs from the batch
+ * path in rounding).  RB_ERR_CODE_TYPE when k-1 > max of the code type. */
+rb_status rb_pq_quantize_vector(const rb_pq *pq, const float *x, ptrdiff_t x_stride, void *codes,
+                                int code_width, ptrdiff_t code_stride, int mem_kind, void *stream);
+
+/* ---- Reconstruct (src/pq/traits.rs:102-156; impl pq.rs:305-348) ------------------------------- */
+
+/* reconstruct_batch_into  pq.rs:309-327 -> primitives.rs:150-173 (+ out = out . R^T).  RB_ERR_CODE_RANGE
+ * if any code >= k (detected on the device; output rows with a bad code are unspecified). */
+rb_status rb_pq_reconstruct_batch(const rb_pq *pq, const void *codes, int code_width, size_t n,
+                                  ptrdiff_t code_row_stride, ptrdiff_t code_col_stride, float *out,
+                                  ptrdiff_t out_row_stride, ptrdiff_t out_col_stride, int mem_kind,
+                                  void *stream);
+/* reconstruct_into  pq.rs:329-343 -> primitives.rs:110-148. */
+rb_status rb_pq_reconstruct(const rb_pq *pq, const void *codes, int code_width, ptrdiff_t code_stride,
+                            float *out, ptrdiff_t out_stride, int mem_kind, void *stream);
+
+/* ---- TrainPq (src/pq/traits.rs:15-72; impl pq.rs:196-250) and k-means (src/kmeans.rs) --------- */
+
+/* Pq::check_quantizer_invariants  pq.rs:63-100 (host only).  *detail (may be NULL) receives
+ * max_subquantizer_bits / max_subquantizers for the two errors that carry one. */
+rb_status rb_check_quantizer_invariants(size_t n_subquantizers, uint32_t n_subquantizer_bits,
+                                        size_t n_iterations, size_t n_attempts, size_t n_rows,
+                                        size_t n_cols, uint64_t *detail);
+
+/* Length (in floats) of the packed per-iteration accumulator:
+ * sums [M,k,dsub] | counts [M,k] | sum of squared norms [M].  This is the all-reduce payload of
+ * data-parallel k-means. */
+size_t rb_kmeans_packed_len(size_t n_subquantizers, size_t n_centroids, size_t subquantizer_dim);
+
+/* First half of KMeansIteration::kmeans_iteration for all M subquantizers at once (kmeans.rs:319-325):
+ * cluster_assignments (kmeans.rs:133-159) of the LOCAL rows against `centroids`, then the scatter-add
+ * of update_centroids (kmeans.rs:181-189) into `packed` (zeroed by this call).  All pointers are
+ * DEVICE memory.  x: [n_local, d] with row stride x_row_stride (col stride 1). */
+rb_status rb_kmeans_assign_accumulate(const float *x, size_t n_local, ptrdiff_t x_row_stride,
+                                      const float *centroids, size_t n_subquantizers,
+                                      size_t n_centroids, size_t subquantizer_dim, float *packed,
+                                      void *stream);
+/* Second half (kmeans.rs:191-197 + mean_squared_error kmeans.rs:330-360): divide non-empty clusters,
+ * leave empty clusters at zero, write the new centroids and, if loss_or_null != NULL, the per-
+ * subquantizer mean squared error of the new centroids under the old assignments (computed from the
+ * accumulated moments in FP64).  `packed` holds the (all-reduced) sums over n_total rows.  DEVICE memory. */
+rb_status rb_kmeans_finalize(const float *packed, size_t n_subquantizers, size_t n_centroids,
+                             size_t subquantizer_dim, uint64_t n_total, float *centroids,
+                             float *loss_or_null, void *stream);
+
+/* TrainPq::train_pq_using for Pq  pq.rs:201-249 with the initial centroids supplied by the caller
+ * (initial: HOST [n_attempts, M, k, dsub]; the reference draws them with RandomInstanceCentroids,
+ * kmeans.rs:52-87, whose HashSet iteration order is not reproducible, so they stay a host-side input).
+ * instances: [n, d] (mem_kind).  loss_out: HOST [M] or NULL.  Best of n_attempts by loss (pq.rs:183-187). */
+rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t row_stride,
+                      ptrdiff_t col_stride, size_t n_subquantizers, uint32_t n_subquantizer_bits,
+                      size_t n_iterations, size_t n_attempts, const float *initial_centroids,
+                      float *loss_out, int mem_kind, void *stream, rb_pq **out);
+
+/* ---- projection (pq.rs:276, pq.rs:323-326; opq.rs:68,173) ------------------------------------- */
+
+/* out[n,d] = x[n,d] . R (transpose_r = 0) or x . R^T (transpose_r = 1) with the reference's FP32
+ * accumulation order (sequential FMA over k, kc = 256 blocks).  DEVICE memory; out row-major. */
+rb_status rb_project_rows(const float *x, size_t n, size_t d, ptrdiff_t x_row_stride,
+                          ptrdiff_t x_col_stride, const float *r_dev, int transpose_r, float *out,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REDUCTIVE_B200_H */

@@ -1,0 +1,708 @@
+// cabi.cu — implementation of include/reductive_b200.h: handle management, layout normalisation at the
+// boundary, host<->device pipelines and the k-means training loop.  All arithmetic happens in the CUDA
+// kernels of this directory; there is no CPU compute path here (only copies, packing of odd strides and
+// the best-of-attempts selection on M floats).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "encode_tc.cuh"
+
+namespace rb {
+
+std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_encode_algo{RB_ENCODE_AUTO};
+static thread_local char t_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+static rb_status fail(rb_status s, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return s;
+}
+
+static rb_status require_device()
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return fail(RB_ERR_NO_DEVICE,
+                    "no CUDA device visible (%s); reductive_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    static std::once_flag once[64];
+    int dev = 0;
+    RB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64) {
+        std::call_once(once[dev], [dev]() {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t thr = UINT64_MAX;  // keep freed workspaces cached in the pool
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+        });
+    }
+    return RB_OK;
+}
+
+// Stream-ordered workspace that frees itself.
+struct Workspace {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    rb_status alloc(size_t bytes, cudaStream_t stream)
+    {
+        s = stream;
+        RB_CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 1, stream));
+        return RB_OK;
+    }
+    ~Workspace()
+    {
+        if (p) cudaFreeAsync(p, s);
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace rb
+
+using namespace rb;
+
+struct rb_pq {
+    int device = 0;
+    size_t M = 0, k = 0, dsub = 0, d = 0;
+    float *q_dev = nullptr;     // [M,k,dsub]
+    float *cs_dev = nullptr;    // [M,k]
+    float *proj_dev = nullptr;  // [d,d] or null
+    TensorOperands tc;          // bf16-split codebook for the tcgen05 path (may be empty)
+    std::vector<float> q_host, proj_host;
+    DeviceCodebook cb() const { return DeviceCodebook{q_dev, cs_dev, M, k, dsub}; }
+};
+
+static bool valid_width(int w) { return w == 1 || w == 2 || w == 4 || w == 8; }
+
+// ---------------------------------------------------------------------------------------------------
+// encode on device-resident, row-major-with-pitch data
+// ---------------------------------------------------------------------------------------------------
+static rb_status encode_device(const DeviceCodebook &cb, const TensorOperands *tc, const float *x, size_t n,
+                               ptrdiff_t ldx, int seq_norm, void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs,
+                               cudaStream_t stream)
+{
+    int algo = g_encode_algo.load();
+    const bool tc_ok = tc != nullptr && tc->ready() && !seq_norm && tensor_path_supported(cb);
+    if (algo == RB_ENCODE_TENSOR && !tc_ok)
+        return fail(RB_ERR_UNSUPPORTED, "tensor encode path does not cover this shape (k=%zu, dsub=%zu)", cb.k, cb.dsub);
+    if (algo == RB_ENCODE_AUTO) algo = tc_ok ? RB_ENCODE_TENSOR : RB_ENCODE_EXACT;
+    if (algo == RB_ENCODE_TENSOR)
+        return launch_encode_tensor(cb, *tc, x, n, ldx, codes, code_width, crs, ccs, stream);
+    return launch_encode_exact(cb, x, n, ldx, codes, code_width, crs, ccs, seq_norm, stream);
+}
+
+// rows per workspace chunk so that a [rows, d] f32 temporary stays around 1 GiB
+static size_t workspace_rows(size_t n, size_t d)
+{
+    size_t rows = ((size_t)1 << 30) / (d * sizeof(float));
+    if (rows < 1024) rows = 1024;
+    return rows < n ? rows : n;
+}
+
+static rb_status quantize_batch_device(const rb_pq *pq, const float *x, size_t n, ptrdiff_t rs, ptrdiff_t cs,
+                                       void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream)
+{
+    const size_t d = pq->d;
+    const DeviceCodebook cb = pq->cb();
+    if (!pq->proj_dev && cs == 1) {  // primitives.rs:96: column slices of a standard-layout view
+        return encode_device(cb, &pq->tc, x, n, rs, 0, codes, code_width, crs, ccs, stream);
+    }
+    const size_t chunk = workspace_rows(n, d);
+    Workspace ws;
+    RB_TRY(ws.alloc(chunk * d * sizeof(float), stream));
+    for (size_t r0 = 0; r0 < n; r0 += chunk) {
+        const size_t rows = n - r0 < chunk ? n - r0 : chunk;
+        const float *xs = x + (ptrdiff_t)r0 * rs;
+        int seq_norm = 0;
+        if (pq->proj_dev) {  // pq.rs:276: rx = x.dot(projection), a fresh standard-layout array
+            RB_TRY(launch_project(xs, rows, d, rs, cs, pq->proj_dev, 0, ws.as<float>(), stream));
+        } else {  // non-unit column stride: pack; the reference's row norms take the sequential dot then
+            RB_TRY(launch_pack_rows(xs, rows, d, rs, cs, ws.as<float>(), stream));
+            seq_norm = (d > 1 && pq->dsub > 1) ? 1 : 0;
+        }
+        char *cdst = reinterpret_cast<char *>(codes) + (ptrdiff_t)r0 * crs * code_width;
+        RB_TRY(encode_device(cb, &pq->tc, ws.as<float>(), rows, (ptrdiff_t)d, seq_norm, cdst, code_width, crs, ccs,
+                             stream));
+    }
+    return RB_OK;
+}
+
+static rb_status reconstruct_batch_device(const rb_pq *pq, const void *codes, int code_width, size_t n, ptrdiff_t crs,
+                                          ptrdiff_t ccs, float *out, ptrdiff_t ors, ptrdiff_t ocs, int *err_flag,
+                                          cudaStream_t stream)
+{
+    const size_t d = pq->d;
+    const DeviceCodebook cb = pq->cb();
+    if (!pq->proj_dev && ocs == 1)
+        return launch_gather(cb, codes, code_width, n, crs, ccs, out, ors, err_flag, stream);
+    const size_t chunk = workspace_rows(n, d);
+    Workspace y, z;
+    RB_TRY(y.alloc(chunk * d * sizeof(float), stream));
+    const bool direct = pq->proj_dev && ocs == 1 && ors == (ptrdiff_t)d;
+    if (pq->proj_dev && !direct) RB_TRY(z.alloc(chunk * d * sizeof(float), stream));
+    for (size_t r0 = 0; r0 < n; r0 += chunk) {
+        const size_t rows = n - r0 < chunk ? n - r0 : chunk;
+        const char *csrc = reinterpret_cast<const char *>(codes) + (ptrdiff_t)r0 * crs * code_width;
+        float *odst = out + (ptrdiff_t)r0 * ors;
+        RB_TRY(launch_gather(cb, csrc, code_width, rows, crs, ccs, y.as<float>(), (ptrdiff_t)d, err_flag, stream));
+        if (pq->proj_dev) {  // pq.rs:323-326: reconstructions.dot(&projection.t()), then assign
+            float *pdst = direct ? odst : z.as<float>();
+            RB_TRY(launch_project(y.as<float>(), rows, d, (ptrdiff_t)d, 1, pq->proj_dev, 1, pdst, stream));
+            if (!direct) RB_TRY(launch_unpack_rows(z.as<float>(), rows, d, odst, ors, ocs, stream));
+        } else {
+            RB_TRY(launch_unpack_rows(y.as<float>(), rows, d, odst, ors, ocs, stream));
+        }
+    }
+    return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-memory pipelines: chunked, double-buffered H2D -> kernels -> D2H
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct HostPipe {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    rb_status init()
+    {
+        for (int i = 0; i < 2; i++) RB_CUDA_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        return RB_OK;
+    }
+    ~HostPipe()
+    {
+        for (int i = 0; i < 2; i++)
+            if (st[i]) {
+                cudaStreamSynchronize(st[i]);
+                cudaStreamDestroy(st[i]);
+            }
+    }
+};
+
+size_t host_chunk_rows(size_t n, size_t row_bytes)
+{
+    size_t rows = ((size_t)64 << 20) / (row_bytes ? row_bytes : 1);
+    if (rows < 4096) rows = 4096;
+    return rows < n ? rows : n;
+}
+
+// dense copy of a strided host matrix of `elem` byte elements into dst [rows, cols]
+void host_pack(const void *src, size_t rows, size_t cols, ptrdiff_t rs, ptrdiff_t cs, size_t elem, void *dst)
+{
+    const char *s = reinterpret_cast<const char *>(src);
+    char *d = reinterpret_cast<char *>(dst);
+    for (size_t r = 0; r < rows; r++)
+        for (size_t c = 0; c < cols; c++)
+            memcpy(d + (r * cols + c) * elem, s + ((ptrdiff_t)r * rs + (ptrdiff_t)c * cs) * (ptrdiff_t)elem, elem);
+}
+
+void host_unpack(const void *src, size_t rows, size_t cols, void *dst, ptrdiff_t rs, ptrdiff_t cs, size_t elem)
+{
+    const char *s = reinterpret_cast<const char *>(src);
+    char *d = reinterpret_cast<char *>(dst);
+    for (size_t r = 0; r < rows; r++)
+        for (size_t c = 0; c < cols; c++)
+            memcpy(d + ((ptrdiff_t)r * rs + (ptrdiff_t)c * cs) * (ptrdiff_t)elem, s + (r * cols + c) * elem, elem);
+}
+
+}  // namespace
+
+static rb_status quantize_batch_host(const rb_pq *pq, const float *x, size_t n, ptrdiff_t rs, ptrdiff_t cs,
+                                     void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs)
+{
+    const size_t d = pq->d, M = pq->M;
+    const bool in2d = (cs == 1 && rs >= (ptrdiff_t)d);
+    const bool out2d = (ccs == 1 && crs >= (ptrdiff_t)M);
+    const size_t chunk = host_chunk_rows(n, d * sizeof(float));
+    HostPipe pipe;
+    RB_TRY(pipe.init());
+    Workspace xin[2], cout[2];
+    std::vector<float> xstage[2];
+    std::vector<unsigned char> cstage[2];
+    for (int i = 0; i < 2; i++) {
+        RB_TRY(xin[i].alloc(chunk * d * sizeof(float), pipe.st[i]));
+        RB_TRY(cout[i].alloc(chunk * M * code_width, pipe.st[i]));
+    }
+    // a strided host view keeps its meaning: without a projection the reference's row norms take the
+    // sequential dot for non-unit column strides (see oracle.c); packing does not change that.
+    const int seq_norm = (!pq->proj_dev && cs != 1 && d > 1 && pq->dsub > 1) ? 1 : 0;
+    size_t pending_r0[2] = {0, 0}, pending_rows[2] = {0, 0};
+    auto drain = [&](int slot) -> rb_status {
+        if (pending_rows[slot] && !out2d) {
+            RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[slot]));
+            host_unpack(cstage[slot].data(), pending_rows[slot], M,
+                        reinterpret_cast<char *>(codes) + (ptrdiff_t)pending_r0[slot] * crs * code_width, crs, ccs,
+                        (size_t)code_width);
+        }
+        pending_rows[slot] = 0;
+        return RB_OK;
+    };
+    int slot = 0;
+    for (size_t r0 = 0; r0 < n; r0 += chunk, slot ^= 1) {
+        const size_t rows = n - r0 < chunk ? n - r0 : chunk;
+        cudaStream_t st = pipe.st[slot];
+        RB_TRY(drain(slot));
+        float *xd = xin[slot].as<float>();
+        if (in2d) {
+            RB_CUDA_TRY(cudaMemcpy2DAsync(xd, d * sizeof(float), x + (ptrdiff_t)r0 * rs, (size_t)rs * sizeof(float),
+                                          d * sizeof(float), rows, cudaMemcpyHostToDevice, st));
+        } else {
+            RB_CUDA_TRY(cudaStreamSynchronize(st));  // staging buffer of this slot is free again
+            xstage[slot].resize(rows * d);
+            host_pack(x + (ptrdiff_t)r0 * rs, rows, d, rs, cs, sizeof(float), xstage[slot].data());
+            RB_CUDA_TRY(cudaMemcpyAsync(xd, xstage[slot].data(), rows * d * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
+        const float *src = xd;
+        Workspace rx;
+        if (pq->proj_dev) {
+            RB_TRY(rx.alloc(rows * d * sizeof(float), st));
+            RB_TRY(launch_project(xd, rows, d, (ptrdiff_t)d, 1, pq->proj_dev, 0, rx.as<float>(), st));
+            src = rx.as<float>();
+        }
+        RB_TRY(encode_device(pq->cb(), &pq->tc, src, rows, (ptrdiff_t)d, seq_norm, cout[slot].p, code_width,
+                             (ptrdiff_t)M, 1, st));
+        if (out2d) {
+            RB_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<char *>(codes) + (ptrdiff_t)r0 * crs * code_width,
+                                          (size_t)crs * code_width, cout[slot].p, M * code_width, M * code_width, rows,
+                                          cudaMemcpyDeviceToHost, st));
+        } else {
+            cstage[slot].resize(rows * M * code_width);
+            RB_CUDA_TRY(cudaMemcpyAsync(cstage[slot].data(), cout[slot].p, rows * M * code_width,
+                                        cudaMemcpyDeviceToHost, st));
+            pending_r0[slot] = r0;
+            pending_rows[slot] = rows;
+        }
+    }
+    for (int i = 0; i < 2; i++) {
+        RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[i]));
+        RB_TRY(drain(i));
+    }
+    return RB_OK;
+}
+
+static rb_status reconstruct_batch_host(const rb_pq *pq, const void *codes, int code_width, size_t n, ptrdiff_t crs,
+                                        ptrdiff_t ccs, float *out, ptrdiff_t ors, ptrdiff_t ocs)
+{
+    const size_t d = pq->d, M = pq->M;
+    const bool in2d = (ccs == 1 && crs >= (ptrdiff_t)M);
+    const bool out2d = (ocs == 1 && ors >= (ptrdiff_t)d);
+    const size_t chunk = host_chunk_rows(n, d * sizeof(float));
+    HostPipe pipe;
+    RB_TRY(pipe.init());
+    Workspace cin[2], yout[2], flag;
+    std::vector<unsigned char> cstage[2];
+    std::vector<float> ystage[2];
+    for (int i = 0; i < 2; i++) {
+        RB_TRY(cin[i].alloc(chunk * M * code_width, pipe.st[i]));
+        RB_TRY(yout[i].alloc(chunk * d * sizeof(float), pipe.st[i]));
+    }
+    RB_TRY(flag.alloc(sizeof(int), pipe.st[0]));
+    RB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int), pipe.st[0]));
+    RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[0]));
+    size_t pending_r0[2] = {0, 0}, pending_rows[2] = {0, 0};
+    auto drain = [&](int slot) -> rb_status {
+        if (pending_rows[slot] && !out2d) {
+            RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[slot]));
+            host_unpack(ystage[slot].data(), pending_rows[slot], d, out + (ptrdiff_t)pending_r0[slot] * ors, ors, ocs,
+                        sizeof(float));
+        }
+        pending_rows[slot] = 0;
+        return RB_OK;
+    };
+    int slot = 0;
+    for (size_t r0 = 0; r0 < n; r0 += chunk, slot ^= 1) {
+        const size_t rows = n - r0 < chunk ? n - r0 : chunk;
+        cudaStream_t st = pipe.st[slot];
+        RB_TRY(drain(slot));
+        const char *csrc = reinterpret_cast<const char *>(codes) + (ptrdiff_t)r0 * crs * code_width;
+        if (in2d) {
+            RB_CUDA_TRY(cudaMemcpy2DAsync(cin[slot].p, M * code_width, csrc, (size_t)crs * code_width, M * code_width,
+                                          rows, cudaMemcpyHostToDevice, st));
+        } else {
+            RB_CUDA_TRY(cudaStreamSynchronize(st));
+            cstage[slot].resize(rows * M * code_width);
+            host_pack(csrc, rows, M, crs, ccs, (size_t)code_width, cstage[slot].data());
+            RB_CUDA_TRY(cudaMemcpyAsync(cin[slot].p, cstage[slot].data(), rows * M * code_width,
+                                        cudaMemcpyHostToDevice, st));
+        }
+        RB_TRY(reconstruct_batch_device(pq, cin[slot].p, code_width, rows, (ptrdiff_t)M, 1, yout[slot].as<float>(),
+                                        (ptrdiff_t)d, 1, flag.as<int>(), st));
+        if (out2d) {
+            RB_CUDA_TRY(cudaMemcpy2DAsync(out + (ptrdiff_t)r0 * ors, (size_t)ors * sizeof(float), yout[slot].p,
+                                          d * sizeof(float), d * sizeof(float), rows, cudaMemcpyDeviceToHost, st));
+        } else {
+            ystage[slot].resize(rows * d);
+            RB_CUDA_TRY(cudaMemcpyAsync(ystage[slot].data(), yout[slot].p, rows * d * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st));
+            pending_r0[slot] = r0;
+            pending_rows[slot] = rows;
+        }
+    }
+    for (int i = 0; i < 2; i++) {
+        RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[i]));
+        RB_TRY(drain(i));
+    }
+    int bad = 0;
+    RB_CUDA_TRY(cudaMemcpy(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) return fail(RB_ERR_CODE_RANGE, "a code is >= the number of centroids (%zu)", pq->k);
+    return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *rb_last_error_message(void) { return t_err; }
+int rb_abi_version(void) { return RB_ABI_VERSION; }
+uint64_t rb_kernel_launch_count(void) { return g_launches.load(); }
+
+rb_status rb_set_encode_algo(int algo)
+{
+    if (algo != RB_ENCODE_AUTO && algo != RB_ENCODE_EXACT && algo != RB_ENCODE_TENSOR)
+        return fail(RB_ERR_INVALID, "unknown encode algo %d", algo);
+    g_encode_algo.store(algo);
+    return RB_OK;
+}
+
+rb_status rb_pq_create(const float *quantizers, size_t M, size_t k, size_t dsub, const float *projection,
+                       rb_pq **out)
+{
+    if (!out) return fail(RB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!quantizers) return fail(RB_ERR_INVALID, "quantizers is NULL");
+    if (M == 0 || k == 0 || dsub == 0)  // pq.rs:39-42
+        return fail(RB_ERR_SHAPE, "Attempted to construct a product quantizer without quantizers.");
+    RB_TRY(require_device());
+    rb_pq *pq = new rb_pq();
+    pq->M = M; pq->k = k; pq->dsub = dsub; pq->d = M * dsub;
+    cudaGetDevice(&pq->device);
+    const size_t qn = M * k * dsub;
+    pq->q_host.assign(quantizers, quantizers + qn);
+    rb_status st = RB_OK;
+    auto body = [&]() -> rb_status {
+        RB_CUDA_TRY(cudaMalloc(&pq->q_dev, qn * sizeof(float)));
+        RB_CUDA_TRY(cudaMalloc(&pq->cs_dev, M * k * sizeof(float)));
+        RB_CUDA_TRY(cudaMemcpy(pq->q_dev, quantizers, qn * sizeof(float), cudaMemcpyHostToDevice));
+        RB_TRY(launch_centroid_norms(pq->q_dev, M * k, dsub, pq->cs_dev, nullptr));
+        if (projection) {
+            pq->proj_host.assign(projection, projection + pq->d * pq->d);
+            RB_CUDA_TRY(cudaMalloc(&pq->proj_dev, pq->d * pq->d * sizeof(float)));
+            RB_CUDA_TRY(cudaMemcpy(pq->proj_dev, projection, pq->d * pq->d * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        RB_TRY(pq->tc.prepare(pq->cb(), nullptr));
+        RB_CUDA_TRY(cudaStreamSynchronize(nullptr));
+        return RB_OK;
+    };
+    st = body();
+    if (st != RB_OK) {
+        rb_pq_destroy(pq);
+        return st;
+    }
+    *out = pq;
+    return RB_OK;
+}
+
+void rb_pq_destroy(rb_pq *pq)
+{
+    if (!pq) return;
+    pq->tc.release();
+    cudaFree(pq->q_dev);
+    cudaFree(pq->cs_dev);
+    cudaFree(pq->proj_dev);
+    delete pq;
+}
+
+size_t rb_pq_quantized_len(const rb_pq *pq) { return pq ? pq->M : 0; }
+size_t rb_pq_reconstructed_len(const rb_pq *pq) { return pq ? pq->d : 0; }
+size_t rb_pq_n_quantizer_centroids(const rb_pq *pq) { return pq ? pq->k : 0; }
+int rb_pq_has_projection(const rb_pq *pq) { return pq && pq->proj_dev ? 1 : 0; }
+
+rb_status rb_pq_subquantizers(const rb_pq *pq, float *out_host)
+{
+    if (!pq || !out_host) return fail(RB_ERR_INVALID, "NULL argument");
+    memcpy(out_host, pq->q_host.data(), pq->q_host.size() * sizeof(float));
+    return RB_OK;
+}
+
+rb_status rb_pq_projection(const rb_pq *pq, float *out_host)
+{
+    if (!pq || !out_host) return fail(RB_ERR_INVALID, "NULL argument");
+    if (pq->proj_host.empty()) return fail(RB_ERR_INVALID, "quantizer has no projection");
+    memcpy(out_host, pq->proj_host.data(), pq->proj_host.size() * sizeof(float));
+    return RB_OK;
+}
+
+rb_status rb_pq_quantize_batch(const rb_pq *pq, const float *x, size_t n, ptrdiff_t rs, ptrdiff_t cs, void *codes,
+                               int code_width, ptrdiff_t crs, ptrdiff_t ccs, int mem_kind, void *stream)
+{
+    if (!pq) return fail(RB_ERR_INVALID, "pq is NULL");
+    if (!valid_width(code_width)) return fail(RB_ERR_INVALID, "code_width must be 1, 2, 4 or 8");
+    if (mem_kind != RB_MEM_HOST && mem_kind != RB_MEM_DEVICE) return fail(RB_ERR_INVALID, "bad mem_kind");
+    if (n == 0) return RB_OK;
+    if (!x || !codes) return fail(RB_ERR_INVALID, "NULL data pointer");
+    RB_TRY(require_device());
+    if (mem_kind == RB_MEM_DEVICE)
+        return quantize_batch_device(pq, x, n, rs, cs, codes, code_width, crs, ccs, (cudaStream_t)stream);
+    return quantize_batch_host(pq, x, n, rs, cs, codes, code_width, crs, ccs);
+}
+
+rb_status rb_pq_quantize_vector(const rb_pq *pq, const float *x, ptrdiff_t sx, void *codes, int code_width,
+                                ptrdiff_t cstride, int mem_kind, void *stream)
+{
+    if (!pq || !x || !codes) return fail(RB_ERR_INVALID, "NULL argument");
+    if (!valid_width(code_width)) return fail(RB_ERR_INVALID, "code_width must be 1, 2, 4 or 8");
+    if (code_width < 8) {  // primitives.rs:31-34
+        const uint64_t maxv = code_width == 1 ? 0xffull : code_width == 2 ? 0xffffull : 0xffffffffull;
+        if ((uint64_t)(pq->k - 1) > maxv)
+            return fail(RB_ERR_CODE_TYPE, "Cannot store centroids in quantizer index type");
+    }
+    RB_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t d = pq->d, M = pq->M;
+    Workspace scratch;
+    RB_TRY(scratch.alloc(d * sizeof(float), st));
+    if (mem_kind == RB_MEM_DEVICE)
+        return launch_quantize_vector(pq->cb(), pq->proj_dev, x, sx, codes, code_width, cstride, scratch.as<float>(), st);
+    Workspace xd, cd;
+    RB_TRY(xd.alloc(d * sizeof(float), st));
+    RB_TRY(cd.alloc(M * code_width, st));
+    std::vector<float> xh(d);
+    for (size_t i = 0; i < d; i++) xh[i] = x[(ptrdiff_t)i * sx];
+    RB_CUDA_TRY(cudaMemcpyAsync(xd.p, xh.data(), d * sizeof(float), cudaMemcpyHostToDevice, st));
+    // the packed copy is contiguous; a strided host view must still take the sequential-dot arithmetic:
+    // pass a fake stride of 2 over a doubled buffer?  No — keep it simple and exact: re-expand on device.
+    Workspace xexp;
+    const float *xin = xd.as<float>();
+    ptrdiff_t xin_stride = 1;
+    if (sx != 1 && !pq->proj_dev && d > 1) {
+        RB_TRY(xexp.alloc(2 * d * sizeof(float), st));
+        RB_CUDA_TRY(cudaMemcpy2DAsync(xexp.p, 2 * sizeof(float), xd.p, sizeof(float), sizeof(float), d,
+                                      cudaMemcpyDeviceToDevice, st));
+        xin = xexp.as<float>();
+        xin_stride = 2;
+    }
+    RB_TRY(launch_quantize_vector(pq->cb(), pq->proj_dev, xin, xin_stride, cd.p, code_width, 1, scratch.as<float>(), st));
+    std::vector<unsigned char> ch(M * code_width);
+    RB_CUDA_TRY(cudaMemcpyAsync(ch.data(), cd.p, M * code_width, cudaMemcpyDeviceToHost, st));
+    RB_CUDA_TRY(cudaStreamSynchronize(st));
+    host_unpack(ch.data(), M, 1, codes, cstride, 1, (size_t)code_width);
+    return RB_OK;
+}
+
+rb_status rb_pq_reconstruct_batch(const rb_pq *pq, const void *codes, int code_width, size_t n, ptrdiff_t crs,
+                                  ptrdiff_t ccs, float *out, ptrdiff_t ors, ptrdiff_t ocs, int mem_kind, void *stream)
+{
+    if (!pq) return fail(RB_ERR_INVALID, "pq is NULL");
+    if (!valid_width(code_width)) return fail(RB_ERR_INVALID, "code_width must be 1, 2, 4 or 8");
+    if (mem_kind != RB_MEM_HOST && mem_kind != RB_MEM_DEVICE) return fail(RB_ERR_INVALID, "bad mem_kind");
+    if (n == 0) return RB_OK;
+    if (!codes || !out) return fail(RB_ERR_INVALID, "NULL data pointer");
+    RB_TRY(require_device());
+    if (mem_kind == RB_MEM_HOST) return reconstruct_batch_host(pq, codes, code_width, n, crs, ccs, out, ors, ocs);
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace flag;
+    RB_TRY(flag.alloc(sizeof(int), st));
+    RB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    RB_TRY(reconstruct_batch_device(pq, codes, code_width, n, crs, ccs, out, ors, ocs, flag.as<int>(), st));
+    int bad = 0;  // reporting an out-of-range code needs the result: this call synchronises `stream`
+    RB_CUDA_TRY(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (bad) return fail(RB_ERR_CODE_RANGE, "a code is >= the number of centroids (%zu)", pq->k);
+    return RB_OK;
+}
+
+rb_status rb_pq_reconstruct(const rb_pq *pq, const void *codes, int code_width, ptrdiff_t cstride, float *out,
+                            ptrdiff_t ostride, int mem_kind, void *stream)
+{
+    if (!pq || !codes || !out) return fail(RB_ERR_INVALID, "NULL argument");
+    if (!valid_width(code_width)) return fail(RB_ERR_INVALID, "code_width must be 1, 2, 4 or 8");
+    RB_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t d = pq->d, M = pq->M;
+    Workspace scratch, flag;
+    RB_TRY(scratch.alloc(d * sizeof(float), st));
+    RB_TRY(flag.alloc(sizeof(int), st));
+    RB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    int bad = 0;
+    if (mem_kind == RB_MEM_DEVICE) {
+        RB_TRY(launch_reconstruct_vector(pq->cb(), pq->proj_dev, codes, code_width, cstride, out, ostride,
+                                         scratch.as<float>(), flag.as<int>(), st));
+    } else {
+        Workspace cd, od;
+        RB_TRY(cd.alloc(M * code_width, st));
+        RB_TRY(od.alloc(d * sizeof(float), st));
+        std::vector<unsigned char> ch(M * code_width);
+        host_pack(codes, M, 1, cstride, 1, (size_t)code_width, ch.data());
+        RB_CUDA_TRY(cudaMemcpyAsync(cd.p, ch.data(), M * code_width, cudaMemcpyHostToDevice, st));
+        RB_TRY(launch_reconstruct_vector(pq->cb(), pq->proj_dev, cd.p, code_width, 1, od.as<float>(), 1,
+                                         scratch.as<float>(), flag.as<int>(), st));
+        std::vector<float> oh(d);
+        RB_CUDA_TRY(cudaMemcpyAsync(oh.data(), od.p, d * sizeof(float), cudaMemcpyDeviceToHost, st));
+        RB_CUDA_TRY(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RB_CUDA_TRY(cudaStreamSynchronize(st));
+        if (!bad)
+            for (size_t i = 0; i < d; i++) out[(ptrdiff_t)i * ostride] = oh[i];
+    }
+    if (mem_kind == RB_MEM_DEVICE) {
+        RB_CUDA_TRY(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RB_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    if (bad) return fail(RB_ERR_CODE_RANGE, "a code is >= the number of centroids (%zu)", pq->k);
+    return RB_OK;
+}
+
+rb_status rb_check_quantizer_invariants(size_t n_subquantizers, uint32_t n_bits, size_t n_iterations,
+                                        size_t n_attempts, size_t n_rows, size_t n_cols, uint64_t *detail)
+{
+    if (n_subquantizers == 0 || n_subquantizers > n_cols) {  // pq.rs:70-75
+        if (detail) *detail = n_cols;
+        return fail(RB_ERR_N_SUBQUANTIZERS_RANGE, "The number of subquantizers must be between 1 and %zu, was %zu",
+                    n_cols, n_subquantizers);
+    }
+    // pq.rs:77: (nrows as f64).log2().trunc() as u32  (saturating cast: 0 rows -> 0)
+    uint32_t max_bits = 0;
+    for (size_t v = n_rows; v > 1; v >>= 1) max_bits++;
+    if (n_bits == 0 || n_bits > max_bits) {  // pq.rs:78-82
+        if (detail) *detail = max_bits;
+        return fail(RB_ERR_N_SUBQUANTIZER_BITS, "The number of subquantizers bits must be between 1 and %u", max_bits);
+    }
+    if (n_cols % n_subquantizers != 0)  // pq.rs:84-89
+        return fail(RB_ERR_NUMBER_SUBQUANTIZERS,
+                    "The number of columns (%zu) is not exactly dividable by the number of subquantizers (%zu)",
+                    n_cols, n_subquantizers);
+    if (n_iterations == 0)  // pq.rs:91-93
+        return fail(RB_ERR_N_ITERATIONS, "The number of quantization iterations must be >= 1");
+    if (n_attempts == 0)  // pq.rs:95-97
+        return fail(RB_ERR_N_ATTEMPTS, "The number of quantization attempts per iteration must be >= 1");
+    return RB_OK;
+}
+
+size_t rb_kmeans_packed_len(size_t M, size_t k, size_t dsub) { return M * k * dsub + M * k + M; }
+
+rb_status rb_kmeans_assign_accumulate(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids, size_t M,
+                                      size_t k, size_t dsub, float *packed, void *stream)
+{
+    if (!centroids || !packed || (n_local && !x)) return fail(RB_ERR_INVALID, "NULL argument");
+    if (M == 0 || k == 0 || dsub == 0) return fail(RB_ERR_SHAPE, "Cannot cluster instances with zero centroids.");
+    RB_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace cs, codes;
+    RB_TRY(cs.alloc(M * k * sizeof(float), st));
+    RB_TRY(launch_centroid_norms(centroids, M * k, dsub, cs.as<float>(), st));
+    const DeviceCodebook cb{centroids, cs.as<float>(), M, k, dsub};
+    const int width = k <= 256 ? 1 : 4;
+    RB_TRY(codes.alloc(n_local * M * width, st));
+    TensorOperands tc;
+    if (g_encode_algo.load() != RB_ENCODE_EXACT) RB_TRY(tc.prepare(cb, st));
+    rb_status s = encode_device(cb, &tc, x, n_local, ldx, 0, codes.p, width, (ptrdiff_t)M, 1, st);  // kmeans.rs:319
+    if (s == RB_OK)
+        s = launch_kmeans_accumulate(x, n_local, ldx, width == 1 ? codes.as<uint8_t>() : nullptr,
+                                     width == 4 ? codes.as<uint32_t>() : nullptr, M, k, dsub, packed, st);
+    tc.release_async(st);
+    return s;
+}
+
+rb_status rb_kmeans_finalize(const float *packed, size_t M, size_t k, size_t dsub, uint64_t n_total, float *centroids,
+                             float *loss_or_null, void *stream)
+{
+    if (!packed || !centroids) return fail(RB_ERR_INVALID, "NULL argument");
+    RB_TRY(require_device());
+    return launch_kmeans_finalize(packed, M, k, dsub, n_total, centroids, loss_or_null, (cudaStream_t)stream);
+}
+
+rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t rs, ptrdiff_t cs, size_t M,
+                      uint32_t n_bits, size_t n_iterations, size_t n_attempts, const float *initial, float *loss_out,
+                      int mem_kind, void *stream, rb_pq **out)
+{
+    if (!out) return fail(RB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    RB_TRY(rb_check_quantizer_invariants(M, n_bits, n_iterations, n_attempts, n, d, nullptr));  // pq.rs:213-219
+    if (!instances || !initial) return fail(RB_ERR_INVALID, "NULL argument");
+    const size_t k = (size_t)1 << n_bits;  // pq.rs:233
+    if (k >= n)  // kmeans.rs:62-67 (RandomInstanceCentroids asserts k < n)
+        return fail(RB_ERR_K_MEANS_K, "Cannot pick more centroids than instances: %zu instances, %zu centroids", n, k);
+    RB_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t dsub = d / M, qn = M * k * dsub;
+
+    // instances resident and row-major on the device for the whole run
+    Workspace xbuf;
+    const float *x = instances;
+    ptrdiff_t ldx = rs;
+    if (mem_kind == RB_MEM_HOST) {
+        RB_TRY(xbuf.alloc(n * d * sizeof(float), st));
+        if (cs == 1 && rs >= (ptrdiff_t)d) {
+            RB_CUDA_TRY(cudaMemcpy2DAsync(xbuf.p, d * sizeof(float), instances, (size_t)rs * sizeof(float),
+                                          d * sizeof(float), n, cudaMemcpyHostToDevice, st));
+        } else {
+            std::vector<float> tmp(n * d);
+            host_pack(instances, n, d, rs, cs, sizeof(float), tmp.data());
+            RB_CUDA_TRY(cudaMemcpyAsync(xbuf.p, tmp.data(), n * d * sizeof(float), cudaMemcpyHostToDevice, st));
+            RB_CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        x = xbuf.as<float>();
+        ldx = (ptrdiff_t)d;
+    } else if (cs != 1) {
+        RB_TRY(xbuf.alloc(n * d * sizeof(float), st));
+        RB_TRY(launch_pack_rows(instances, n, d, rs, cs, xbuf.as<float>(), st));
+        x = xbuf.as<float>();
+        ldx = (ptrdiff_t)d;
+    }
+
+    Workspace cen, packed, loss_dev;
+    RB_TRY(cen.alloc(qn * sizeof(float), st));
+    RB_TRY(packed.alloc(rb_kmeans_packed_len(M, k, dsub) * sizeof(float), st));
+    RB_TRY(loss_dev.alloc(M * sizeof(float), st));
+    std::vector<float> best_q(qn), cand_q(qn), best_loss(M, 0.f), cand_loss(M, 0.f);
+    for (size_t a = 0; a < n_attempts; a++) {  // pq.rs:168-183, all subquantizers advance together
+        RB_CUDA_TRY(cudaMemcpyAsync(cen.p, initial + a * qn, qn * sizeof(float), cudaMemcpyHostToDevice, st));
+        for (size_t it = 0; it < n_iterations; it++) {  // kmeans.rs:279-284
+            RB_TRY(rb_kmeans_assign_accumulate(x, n, ldx, cen.as<float>(), M, k, dsub, packed.as<float>(), st));
+            RB_TRY(launch_kmeans_finalize(packed.as<float>(), M, k, dsub, n, cen.as<float>(),
+                                          it + 1 == n_iterations ? loss_dev.as<float>() : nullptr, st));
+        }
+        RB_CUDA_TRY(cudaMemcpyAsync(cand_q.data(), cen.p, qn * sizeof(float), cudaMemcpyDeviceToHost, st));
+        RB_CUDA_TRY(cudaMemcpyAsync(cand_loss.data(), loss_dev.p, M * sizeof(float), cudaMemcpyDeviceToHost, st));
+        RB_CUDA_TRY(cudaStreamSynchronize(st));
+        for (size_t m = 0; m < M; m++) {  // pq.rs:184-187: min_by_key(OrderedFloat(loss)) keeps the first minimum
+            const float l = cand_loss[m], b = best_loss[m];
+            const bool less = (l < b) || ((b != b) && (l == l));
+            if (a == 0 || less) {
+                best_loss[m] = l;
+                memcpy(best_q.data() + m * k * dsub, cand_q.data() + m * k * dsub, k * dsub * sizeof(float));
+            }
+        }
+    }
+    if (loss_out) memcpy(loss_out, best_loss.data(), M * sizeof(float));
+    return rb_pq_create(best_q.data(), M, k, dsub, nullptr, out);
+}
+
+rb_status rb_project_rows(const float *x, size_t n, size_t d, ptrdiff_t rs, ptrdiff_t cs, const float *r_dev,
+                          int transpose_r, float *out, void *stream)
+{
+    if ((n && (!x || !out)) || !r_dev) return fail(RB_ERR_INVALID, "NULL argument");
+    RB_TRY(require_device());
+    return launch_project(x, n, d, rs, cs, r_dev, transpose_r, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

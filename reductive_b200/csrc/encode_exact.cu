@@ -1,0 +1,330 @@
+// encode_exact.cu — exact FP32 SIMT nearest-centroid encode (sm_100a).
+//
+// Replaces, bit for bit, the reference chain
+//   primitives::quantize_batch_into   src/pq/primitives.rs:64-104
+//   -> kmeans::cluster_assignments    src/kmeans.rs:133-159
+//   -> SquaredEuclideanDistance<Ix2>  src/linalg.rs:150-180
+// by evaluating, per (row, subquantizer, centroid), the same floating-point expression tree:
+//   xs  = unrolled_dot(x_sub, x_sub)                       (linalg.rs:167)
+//   cs  = unrolled_dot(c_j, c_j)                           (linalg.rs:168, precomputed per codebook)
+//   dp  = fma(x[K-1], c[K-1], ... fma(x[0], c[0], 0))      (linalg.rs:170, matrixmultiply FMA kernel,
+//                                                           kc = 256 blocks combined by a plain add)
+//   d_j = (xs + cs) - (dp + dp)                            (linalg.rs:173-174)
+//   code = first j minimising d_j, NaN ranking largest     (kmeans.rs:150-155)
+// without ever materialising the reference's n x k distance temporary.
+//
+// It is the correctness anchor, the path for shapes the tensor kernel does not cover, and (through
+// launch_encode_recheck) the arbiter of near-ties the tensor kernel flags.
+//
+// Bound: FP32 pipe.  (dsub FMA + ~6 other ops) per (row, m, j) -> at C2 (2M x 300, M=30, k=256)
+// ~2.5e11 lane-ops, i.e. >= 7 ms on 148 SMs x 128 lanes; HBM traffic is the algorithmic 4d+M bytes/row.
+#include "common.cuh"
+
+namespace rb {
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kInvalid = -1;
+
+// Load DSUB floats of one centroid from shared memory with the widest aligned vector loads.
+template <int DSUB>
+__device__ __forceinline__ void load_centroid(const float *__restrict__ src, float (&c)[DSUB])
+{
+    if constexpr (DSUB % 4 == 0) {
+#pragma unroll
+        for (int t = 0; t < DSUB; t += 4) {
+            float4 v = *reinterpret_cast<const float4 *>(src + t);
+            c[t] = v.x; c[t + 1] = v.y; c[t + 2] = v.z; c[t + 3] = v.w;
+        }
+    } else if constexpr (DSUB % 2 == 0) {
+#pragma unroll
+        for (int t = 0; t < DSUB; t += 2) {
+            float2 v = *reinterpret_cast<const float2 *>(src + t);
+            c[t] = v.x; c[t + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < DSUB; t++) c[t] = src[t];
+    }
+}
+
+// Full OrderedFloat semantics for one row (rare path: the fast loop found nothing below +inf).
+template <int DSUB>
+__device__ __noinline__ int slow_argmin(const float *__restrict__ quantizers_m, const float *__restrict__ cs_m,
+                                        int k, const float (&x)[DSUB], float xs)
+{
+    int best = 0;
+    float bv = 0.f;
+    for (int j = 0; j < k; j++) {
+        float dp = 0.f;
+#pragma unroll
+        for (int t = 0; t < DSUB; t++) dp = __fmaf_rn(x[t], quantizers_m[(size_t)j * DSUB + t], dp);
+        float d = ref_distance(xs, cs_m[j], dp);
+        if (j == 0 || of_less(d, bv)) {
+            bv = d;
+            best = j;
+        }
+    }
+    return best;
+}
+
+// One block: kThreads*RPT rows x a range of subquantizers.  Centroids of the current subquantizer are
+// staged in shared memory (in chunks of kch centroids) and broadcast to all lanes.
+template <int DSUB, int RPT>
+__global__ void __launch_bounds__(kThreads)
+encode_exact_kernel(const float *__restrict__ quantizers, const float *__restrict__ cs_all, int M, int k,
+                    int kch, const float *__restrict__ x, long long n, long long ldx, void *codes,
+                    int code_width, long long crs, long long ccs, int seq_norm, int m_per_block)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *cen = smem;                      // [kch][DSUB]
+    float *csm = smem + (size_t)kch * DSUB; // [kch]
+
+    const long long tile_base = (long long)blockIdx.x * (kThreads * RPT);
+    const int m0 = blockIdx.y * m_per_block;
+    const int m1 = min(M, m0 + m_per_block);
+
+    for (int m = m0; m < m1; m++) {
+        const float *qm = quantizers + (size_t)m * k * DSUB;
+        const float *csg = cs_all + (size_t)m * k;
+
+        float xv[RPT][DSUB];
+        float xs[RPT];
+        float best[RPT];
+        int bidx[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+            long long row = tile_base + (long long)r * kThreads + threadIdx.x;
+            if (row < n) {
+                const float *xr = x + row * ldx + (long long)m * DSUB;
+#pragma unroll
+                for (int t = 0; t < DSUB; t++) xv[r][t] = __ldg(xr + t);
+            } else {
+#pragma unroll
+                for (int t = 0; t < DSUB; t++) xv[r][t] = 0.f;
+            }
+            xs[r] = seq_norm ? sequential_sqnorm_reg<DSUB>(xv[r]) : unrolled_sqnorm_reg<DSUB>(xv[r]);
+            best[r] = __int_as_float(0x7f800000);  // +inf
+            bidx[r] = kInvalid;
+        }
+
+        for (int j0 = 0; j0 < k; j0 += kch) {
+            const int jn = min(kch, k - j0);
+            __syncthreads();  // previous chunk fully consumed
+            for (int i = threadIdx.x; i < jn * DSUB; i += kThreads) cen[i] = __ldg(qm + (size_t)j0 * DSUB + i);
+            for (int i = threadIdx.x; i < jn; i += kThreads) csm[i] = __ldg(csg + j0 + i);
+            __syncthreads();
+
+#pragma unroll 2
+            for (int j = 0; j < jn; j++) {
+                float c[DSUB];
+                load_centroid<DSUB>(cen + (size_t)j * DSUB, c);
+                const float csj = csm[j];
+#pragma unroll
+                for (int r = 0; r < RPT; r++) {
+                    float dp = 0.f;
+#pragma unroll
+                    for (int t = 0; t < DSUB; t++) dp = __fmaf_rn(xv[r][t], c[t], dp);
+                    const float d = ref_distance(xs[r], csj, dp);
+                    // strict '<' keeps the first minimum; NaN never wins here (handled below)
+                    if (d < best[r]) {
+                        best[r] = d;
+                        bidx[r] = j0 + j;
+                    }
+                }
+            }
+        }
+
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+            long long row = tile_base + (long long)r * kThreads + threadIdx.x;
+            if (row < n) {
+                int idx = bidx[r];
+                if (idx == kInvalid) idx = slow_argmin<DSUB>(qm, csg, k, xv[r], xs[r]);
+                store_code(codes, code_width, row * crs + (long long)m * ccs, (unsigned)idx);
+            }
+        }
+    }
+}
+
+// Any dsub (including > 256, where the kc = 256 blocking of matrixmultiply matters).  One thread per row,
+// x re-read through L1; slow, only for shapes outside the templated set.
+__global__ void __launch_bounds__(kThreads)
+encode_exact_generic_kernel(const float *__restrict__ quantizers, const float *__restrict__ cs_all, int M, int k,
+                            int dsub, const float *__restrict__ x, long long n, long long ldx, void *codes,
+                            int code_width, long long crs, long long ccs, int seq_norm, int m_per_block)
+{
+    const long long row = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (row >= n) return;
+    const int m0 = blockIdx.y * m_per_block;
+    const int m1 = min(M, m0 + m_per_block);
+    for (int m = m0; m < m1; m++) {
+        const float *qm = quantizers + (size_t)m * k * dsub;
+        const float *csg = cs_all + (size_t)m * k;
+        const float *xr = x + row * ldx + (long long)m * dsub;
+        float xs;
+        if (seq_norm) {
+            xs = 0.f;
+            for (int t = 0; t < dsub; t++) xs = __fadd_rn(xs, __fmul_rn(__ldg(xr + t), __ldg(xr + t)));
+        } else {
+            xs = unrolled_dot_dev(dsub, [&](int i) { return __ldg(xr + i); }, [&](int i) { return __ldg(xr + i); });
+        }
+        int best = 0;
+        float bv = 0.f;
+        for (int j = 0; j < k; j++) {
+            const float *cj = qm + (size_t)j * dsub;
+            float total = 0.f, acc = 0.f;
+            bool have = false;
+            for (int t = 0; t < dsub; t++) {
+                acc = __fmaf_rn(__ldg(xr + t), __ldg(cj + t), acc);
+                if ((t & 255) == 255 || t == dsub - 1) {  // matrixmultiply kc = 256: C = AB, then C = C + AB
+                    total = have ? __fadd_rn(total, acc) : acc;
+                    have = true;
+                    acc = 0.f;
+                }
+            }
+            const float d = ref_distance(xs, __ldg(csg + j), total);
+            if (j == 0 || of_less(d, bv)) {
+                bv = d;
+                best = j;
+            }
+        }
+        store_code(codes, code_width, row * crs + (long long)m * ccs, (unsigned)best);
+    }
+}
+
+__global__ void centroid_norms_kernel(const float *__restrict__ q, size_t rows, int dsub, float *__restrict__ cs)
+{
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *c = q + r * dsub;
+    cs[r] = unrolled_dot_dev(dsub, [&](int i) { return c[i]; }, [&](int i) { return c[i]; });
+}
+
+// One warp per flagged (row, m) pair: lanes stride over centroids with the full reference semantics.
+__global__ void __launch_bounds__(256)
+encode_recheck_kernel(const float *__restrict__ quantizers, const float *__restrict__ cs_all, int k, int dsub,
+                      const float *__restrict__ x, long long ldx, const uint32_t *__restrict__ pairs,
+                      const uint32_t *__restrict__ n_pairs_ptr, uint32_t max_pairs, void *codes, int code_width,
+                      long long crs, long long ccs)
+{
+    const uint32_t n_pairs = min(*n_pairs_ptr, max_pairs);
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < n_pairs; p += warps_per_grid) {
+        const long long row = pairs[2 * (size_t)p];
+        const int m = (int)pairs[2 * (size_t)p + 1];
+        const float *xr = x + row * ldx + (long long)m * dsub;
+        const float *qm = quantizers + (size_t)m * k * dsub;
+        const float *csg = cs_all + (size_t)m * k;
+        const float xs = unrolled_dot_dev(dsub, [&](int i) { return __ldg(xr + i); }, [&](int i) { return __ldg(xr + i); });
+        int best = -1;
+        float bv = 0.f;
+        for (int j = lane; j < k; j += 32) {
+            const float *cj = qm + (size_t)j * dsub;
+            float total = 0.f, acc = 0.f;
+            bool have = false;
+            for (int t = 0; t < dsub; t++) {
+                acc = __fmaf_rn(__ldg(xr + t), __ldg(cj + t), acc);
+                if ((t & 255) == 255 || t == dsub - 1) {
+                    total = have ? __fadd_rn(total, acc) : acc;
+                    have = true;
+                    acc = 0.f;
+                }
+            }
+            const float d = ref_distance(xs, __ldg(csg + j), total);
+            if (best < 0 || of_less(d, bv)) {
+                bv = d;
+                best = j;
+            }
+        }
+        // warp argmin: smaller distance wins, equal distance -> smaller index (first minimum)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, best, off);
+            const bool take = (oi >= 0) && (best < 0 || of_less(ov, bv) || (!of_less(bv, ov) && oi < best));
+            if (take) {
+                bv = ov;
+                best = oi;
+            }
+        }
+        if (lane == 0) store_code(codes, code_width, row * crs + (long long)m * ccs, (unsigned)best);
+    }
+}
+
+template <int DSUB>
+rb_status launch_t(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx, void *codes, int code_width,
+                   ptrdiff_t crs, ptrdiff_t ccs, int seq_norm, cudaStream_t stream)
+{
+    constexpr int RPT = DSUB <= 16 ? 4 : 2;
+    const int k = (int)cb.k, M = (int)cb.M;
+    // centroid chunk so that shared memory stays <= 48 KB (no opt-in needed, several blocks per SM)
+    int kch = (48 * 1024) / ((DSUB + 1) * (int)sizeof(float));
+    kch = kch > k ? k : (kch / 8) * 8;
+    const size_t smem = (size_t)kch * (DSUB + 1) * sizeof(float);
+    const size_t row_tiles = ceil_div(n, (size_t)kThreads * RPT);
+    // enough blocks to fill 148 SMs a few times over: split the subquantizers when there are few row tiles
+    int m_per_block = M;
+    while (m_per_block > 1 && row_tiles * ceil_div(M, m_per_block) < 148 * 4) m_per_block = (m_per_block + 1) / 2;
+    dim3 grid((unsigned)row_tiles, (unsigned)ceil_div(M, m_per_block));
+    encode_exact_kernel<DSUB, RPT><<<grid, kThreads, smem, stream>>>(
+        cb.quantizers, cb.cs, M, k, kch, x, (long long)n, (long long)ldx, codes, code_width, (long long)crs,
+        (long long)ccs, seq_norm, m_per_block);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+}  // namespace
+
+rb_status launch_encode_exact(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx, void *codes,
+                              int code_width, ptrdiff_t crs, ptrdiff_t ccs, int seq_norm, cudaStream_t stream)
+{
+    if (n == 0) return RB_OK;
+    if (cb.k > (size_t)INT32_MAX || cb.M > (size_t)INT32_MAX || cb.dsub > (size_t)INT32_MAX) {
+        set_error("codebook extents exceed 2^31");
+        return RB_ERR_UNSUPPORTED;
+    }
+#define RB_CASE(D) \
+    case D: return launch_t<D>(cb, x, n, ldx, codes, code_width, crs, ccs, seq_norm, stream);
+    switch (cb.dsub) {
+        RB_CASE(1) RB_CASE(2) RB_CASE(3) RB_CASE(4) RB_CASE(5) RB_CASE(6) RB_CASE(7) RB_CASE(8)
+        RB_CASE(9) RB_CASE(10) RB_CASE(12) RB_CASE(15) RB_CASE(16) RB_CASE(20) RB_CASE(24) RB_CASE(25)
+        RB_CASE(30) RB_CASE(32)
+    default: break;
+    }
+#undef RB_CASE
+    const int M = (int)cb.M;
+    const size_t row_tiles = ceil_div(n, (size_t)kThreads);
+    int m_per_block = M;
+    while (m_per_block > 1 && row_tiles * ceil_div(M, m_per_block) < 148 * 4) m_per_block = (m_per_block + 1) / 2;
+    dim3 grid((unsigned)row_tiles, (unsigned)ceil_div(M, m_per_block));
+    encode_exact_generic_kernel<<<grid, kThreads, 0, stream>>>(cb.quantizers, cb.cs, M, (int)cb.k, (int)cb.dsub, x,
+                                                             (long long)n, (long long)ldx, codes, code_width,
+                                                             (long long)crs, (long long)ccs, seq_norm, m_per_block);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+rb_status launch_centroid_norms(const float *quantizers, size_t rows, size_t dsub, float *cs, cudaStream_t stream)
+{
+    if (rows == 0) return RB_OK;
+    centroid_norms_kernel<<<(unsigned)ceil_div(rows, 128), 128, 0, stream>>>(quantizers, rows, (int)dsub, cs);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+rb_status launch_encode_recheck(const DeviceCodebook &cb, const float *x, ptrdiff_t ldx, const uint32_t *pairs,
+                                const uint32_t *n_pairs, uint32_t max_pairs, void *codes, int code_width,
+                                ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream)
+{
+    if (max_pairs == 0) return RB_OK;
+    encode_recheck_kernel<<<148 * 4, 256, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.k, (int)cb.dsub, x,
+                                                        (long long)ldx, pairs, n_pairs, max_pairs, codes, code_width,
+                                                        (long long)crs, (long long)ccs);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+}  // namespace rb

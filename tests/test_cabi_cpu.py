@@ -1,0 +1,123 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol the header declares, the
+host-only entry points agree with the oracle, and compute calls fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import reductive_b200 as rb
+from reductive_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "reductive_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _header_functions()
+    assert declared, "no declarations parsed from the header"
+    assert sorted(_cabi.EXPORTED_SYMBOLS) == declared
+    for name in declared:
+        assert hasattr(_cabi.lib, name), f"{name} is declared in include/reductive_b200.h but not exported"
+    assert _cabi.lib.rb_abi_version() == 1
+
+
+def test_check_quantizer_invariants_matches_oracle(oracle):
+    cases = [(10, 7, 10, 1, 256, 20), (0, 7, 10, 1, 256, 20), (21, 7, 10, 1, 256, 20), (10, 0, 10, 1, 256, 20),
+             (10, 9, 10, 1, 256, 20), (10, 8, 10, 1, 256, 20), (10, 8, 10, 1, 255, 20), (3, 7, 10, 1, 256, 20),
+             (10, 7, 0, 1, 256, 20), (10, 7, 10, 0, 256, 20), (10, 1, 10, 1, 0, 20), (30, 8, 1, 1, 2_000_000, 300),
+             (96, 8, 25, 1, 1_000_000, 768), (7, 3, 1, 1, 9, 7)]
+    for c in cases:
+        want, want_detail = oracle.check_quantizer_invariants(*c)
+        detail = C.c_uint64(0)
+        got = _cabi.lib.rb_check_quantizer_invariants(*c, C.byref(detail))
+        assert got == want, c
+        if want in (3, 5):
+            assert detail.value == want_detail, c
+
+
+def test_error_classes_mirror_reductive_error():
+    with pytest.raises(rb.NSubquantizersOutsideRange):
+        rb.check_quantizer_invariants(0, 7, 10, 1, 256, 20)
+    with pytest.raises(rb.IncorrectNSubquantizerBits):
+        rb.check_quantizer_invariants(10, 9, 10, 1, 256, 20)
+    with pytest.raises(rb.IncorrectNumberSubquantizers):
+        rb.check_quantizer_invariants(3, 7, 10, 1, 256, 20)
+    with pytest.raises(rb.IncorrectNIterations):
+        rb.check_quantizer_invariants(10, 7, 0, 1, 256, 20)
+    with pytest.raises(rb.IncorrectNAttempts):
+        rb.check_quantizer_invariants(10, 7, 10, 0, 256, 20)
+
+
+def test_packed_len():
+    assert _cabi.lib.rb_kmeans_packed_len(96, 256, 8) == 96 * 256 * 8 + 96 * 256 + 96
+
+
+def test_pq_new_panics_like_the_reference():
+    with pytest.raises(rb.ReductivePanic):  # pq.rs:39-42
+        rb.Pq(None, np.zeros((0, 4, 3), np.float32))
+    with pytest.raises(rb.ReductivePanic):  # pq.rs:46-55
+        rb.Pq(np.eye(5, dtype=np.float32), np.zeros((2, 4, 3), np.float32))
+
+
+def test_bucket_eigenvalues():  # opq.rs:303-311
+    assert rb.bucket_eigenvalues(np.array([0.2, 0.6, 0.4, 0.1, 0.3, 0.5]), 3) == [[1, 3], [5, 0], [2, 4]]
+
+
+def test_bucket_large_eigenvalues():  # opq.rs:313-320
+    ev = np.array([11174., 23450., 30835., 1557., 32425., 5154.])
+    assert rb.bucket_eigenvalues(ev, 3) == [[4, 3], [2, 5], [1, 0]]
+
+
+def test_bucket_eigenvalues_uneven():  # opq.rs:322-328 (#[should_panic])
+    with pytest.raises(rb.ReductivePanic):
+        rb.bucket_eigenvalues(np.array([0.2, 0.6, 0.4, 0.1, 0.3, 0.5]), 4)
+
+
+def test_random_instance_centroids_are_distinct_rows():
+    from reductive_b200.pq import random_instance_centroids
+
+    idx = random_instance_centroids((300, 20), 10, 128, 2, np.random.default_rng(0))
+    assert idx.shape == (2, 10, 128)
+    for a in range(2):
+        for m in range(10):
+            assert len(set(idx[a, m].tolist())) == 128 and idx[a, m].min() >= 0 and idx[a, m].max() < 300
+    with pytest.raises(rb.ReductivePanic):  # kmeans.rs:62-67
+        random_instance_centroids((128, 20), 10, 128, 1, np.random.default_rng(0))
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(rb.NoDeviceError):
+        rb.Pq(None, np.ones((2, 4, 3), np.float32))
+    with pytest.raises(rb.NoDeviceError):
+        rb.Pq.train_pq_using(2, 2, 1, 1, np.ones((16, 4), np.float32), np.random.default_rng(0))
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "reductive_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle.h" not in text, f
+
+
+def test_shard_rows_covers_everything():
+    from reductive_b200.dist import shard_rows
+
+    for n in (0, 1, 7, 8, 1000, 2_000_000):
+        for w in (1, 2, 4, 8):
+            spans = [shard_rows(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1

@@ -1,0 +1,87 @@
+"""world_size-2 gloo test of the data-parallel k-means host logic (sharding + one all-reduce per iteration +
+replicated finalize).  The per-rank compute is injected as a numpy restatement of the accumulate/finalize
+kernels so the test runs without a GPU; the CUDA versions are covered by the -m gpu tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.util import normal, rows_as_initial_centroids
+
+
+def _np_local_step(o):
+    def step(x_local, centroids, packed):
+        M, k, dsub = centroids.shape
+        x = x_local.numpy()
+        c = centroids.numpy()
+        sums = np.zeros((M, k, dsub), np.float64)
+        counts = np.zeros((M, k), np.float64)
+        sq = np.zeros((M,), np.float64)
+        for m in range(M):
+            sub = np.ascontiguousarray(x[:, m * dsub:(m + 1) * dsub])
+            a = o.cluster_assignments(c[m], sub).astype(np.int64)
+            np.add.at(sums[m], a, sub.astype(np.float64))
+            np.add.at(counts[m], a, 1.0)
+            sq[m] = (sub.astype(np.float64) ** 2).sum()
+        flat = np.concatenate([sums.ravel(), counts.ravel(), sq]).astype(np.float32)
+        packed.copy_(torch.from_numpy(flat))
+    return step
+
+
+def _np_finalize(packed, n_total, centroids, loss):
+    M, k, dsub = centroids.shape
+    p = packed.numpy().astype(np.float64)
+    sums = p[:M * k * dsub].reshape(M, k, dsub)
+    counts = p[M * k * dsub:M * k * dsub + M * k].reshape(M, k)
+    sq = p[M * k * dsub + M * k:]
+    c = np.where(counts[..., None] > 0, sums / np.maximum(counts[..., None], 1), 0.0)
+    centroids.copy_(torch.from_numpy(c.astype(np.float32)))
+    if loss is not None:
+        sse = sq + (counts[..., None] * c * c - 2 * c * sums).sum(axis=(1, 2))
+        loss.copy_(torch.from_numpy((sse / (n_total * dsub)).astype(np.float32)))
+
+
+def _worker(rank, world, port, n, M, k, dsub, iters, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from reductive_b200.dist import kmeans_data_parallel, shard_rows
+
+    o = orc.get()
+    x = normal((n, M * dsub), 21)
+    init = rows_as_initial_centroids(x, M, k, 22)[0]
+    lo, hi = shard_rows(n, rank, world)
+    cen = torch.from_numpy(init.copy())
+    loss = kmeans_data_parallel(torch.from_numpy(x[lo:hi]), n, cen, iters, local_step=_np_local_step(o),
+                                finalize=_np_finalize)
+    if rank == 0:
+        q.put((cen.numpy(), loss.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_kmeans_world2_matches_single_process(oracle):
+    n, M, k, dsub, iters = 600, 3, 8, 4, 4
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, M, k, dsub, iters, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    cen, loss = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference: the oracle's sequential k-means from the same initial centroids
+    x = normal((n, M * dsub), 21)
+    init = rows_as_initial_centroids(x, M, k, 22)
+    want_q, want_loss = oracle.train_pq(x, M, 3, iters, 1, init)
+    assert np.linalg.norm(cen - want_q) / np.linalg.norm(want_q) < 1e-4
+    assert np.allclose(loss, want_loss, rtol=1e-3)

@@ -1,0 +1,347 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on identical seeded
+inputs.  Bit-exact for codes and Pq reconstructions (integer / copy work), bit-exact as well for the projected
+paths (the FP32 rotation keeps the reference's accumulation order), <= 1e-4 relative for trained centroids.
+
+Every test runs once per encode algorithm (exact SIMT kernel, and AUTO = tensor path where the shape allows)."""
+import numpy as np
+import pytest
+
+import reductive_b200 as rb
+from tests.util import F, near_tie_rows, normal, orthonormal, random_codebook, rows_as_initial_centroids
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["exact", "auto"])
+def algo(request):
+    rb.set_encode_algo(rb.ENCODE_EXACT if request.param == "exact" else rb.ENCODE_AUTO)
+    yield request.param
+    rb.set_encode_algo(rb.ENCODE_AUTO)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "the -m gpu tests need a CUDA device"
+    return torch
+
+
+# ---- the reference's own known-answer vectors, through the CUDA path ----------------------------------
+def _test_vectors():
+    return np.array([[0., 2., 0., -0.5, 0., 0.], [1., -0.2, 0., 0.5, 0.5, 0.],
+                     [-0.2, 0.2, 0., 0., -2., 0.], [1., 0.2, 0., 0., -2., 0.]], F)
+
+
+_QUANT = np.array([[1, 1], [0, 1], [1, 0], [0, 0]])
+_RECON = np.array([[0., 1., 0., 0., 1., 0.], [1., 0., 0., 0., 1., 0.],
+                   [0., 1., 0., 1., -1., 0.], [1., 0., 0., 1., -1., 0.]], F)
+_QUANTIZERS = np.array([[[1., 0., 0.], [0., 1., 0.]], [[1., -1., 0.], [0., 1., 0.]]], F)
+
+
+def test_quantize_batch_with_predefined_codebook(algo):  # pq.rs:409-417
+    pq = rb.Pq(None, _QUANTIZERS)
+    assert np.array_equal(pq.quantize_batch(_test_vectors(), np.uint64), _QUANT)
+
+
+def test_quantize_with_predefined_codebook():  # pq.rs:419-429
+    pq = rb.Pq(None, _QUANTIZERS)
+    for v, q in zip(_test_vectors(), _QUANT):
+        assert np.array_equal(pq.quantize_vector(v, np.uint64), q)
+
+
+def test_reconstruct_batch_with_predefined_codebook():  # pq.rs:471-478
+    pq = rb.Pq(None, _QUANTIZERS)
+    assert np.array_equal(pq.reconstruct_batch(_QUANT.astype(np.uint64)), _RECON)
+
+
+def test_reconstruct_with_predefined_codebook():  # pq.rs:480-490
+    pq = rb.Pq(None, _QUANTIZERS)
+    for q, r in zip(_QUANT.astype(np.uint64), _RECON):
+        assert np.array_equal(pq.reconstruct(q), r)
+
+
+def test_quantizer_lens():  # pq.rs:463-469
+    pq = rb.Pq(None, _QUANTIZERS)
+    assert pq.quantized_len() == 2 and pq.reconstructed_len() == 6 and pq.n_quantizer_centroids() == 2
+    assert np.array_equal(pq.subquantizers(), _QUANTIZERS) and pq.projection() is None
+
+
+def test_quantize_with_type_and_too_narrow_type():  # pq.rs:442-461
+    q = np.random.default_rng(0).random((1, 256, 10), F)
+    rb.Pq(None, q).quantize_vector(np.random.default_rng(1).random((10,), F), np.uint8)
+    q257 = np.random.default_rng(0).random((1, 257, 10), F)
+    with pytest.raises(rb.ReductivePanic):
+        rb.Pq(None, q257).quantize_vector(np.random.default_rng(1).random((10,), F), np.uint8)
+
+
+def test_correct_cluster_assignments_and_update(torch_cuda):  # kmeans.rs:380-435
+    torch = torch_cuda
+    centroids = np.array([[0.5, 0., 0.], [0., -1., 0.], [0., 0., 1.], [0., 1., 1.]], F)
+    instances = np.array([[0., 0.5, 0.], [0., 0., 2.], [1., 0., 0.], [0., 0., 1.],
+                          [0., -2., 0.], [0., 0.7, 0.7], [0., 0., 0.]], F)
+    codes = rb.Pq(None, centroids[None]).quantize_batch(instances, np.uint64)
+    assert codes[:, 0].tolist() == [0, 2, 0, 2, 1, 3, 0]
+    # update_centroids known answer (kmeans.rs:402-435) through one kmeans_iteration from centroids that
+    # reproduce the fixture's assignments [1, 0, 1, 0, 2, 2]
+    inst = np.array([[-1., -1., 0.], [1., 1., 0.], [-2., -1., 0.], [0., 0., 0.], [0., 0., 1.], [0., 0., 2.]], F)
+    cen = torch.tensor([[0.6, 0.6, 0.], [-1.4, -1., 0.], [0., 0., 1.4]], device="cuda")
+    loss = rb.kmeans_iteration(torch.from_numpy(inst).cuda(), cen)
+    assert np.array_equal(cen.cpu().numpy(), np.array([[0.5, 0.5, 0.], [-1.5, -1., 0.], [0., 0., 1.5]], F))
+    assert abs(loss - (0.5 + 0.5 + 0.25 + 0.25 + 0.25 + 0.25) / 18) < 1e-6
+
+
+# ---- random parity against the oracle -------------------------------------------------------------------
+SHAPES = [  # (n, M, k, dsub)
+    (10_000, 10, 256, 30),   # BASELINE config C1
+    (20_000, 30, 256, 10),   # C2 geometry
+    (8_192, 96, 256, 8),     # C3 geometry
+    (16_384, 16, 256, 8),    # C5 geometry
+    (100, 16, 16, 8),        # benches/pq.rs shape
+    (3_001, 4, 64, 7),       # odd dsub, ragged row count
+    (1_234, 3, 100, 11),     # dsub outside the templated set -> generic kernel; k not a multiple of 16
+    (777, 5, 300, 4),        # k > 256
+    (513, 1, 32, 300),       # dsub > 256: the kc = 256 block split
+    (1, 2, 8, 5),            # single row
+]
+
+
+@pytest.mark.parametrize("n,M,k,dsub", SHAPES)
+def test_quantize_and_reconstruct_batch_bit_exact(oracle, algo, n, M, k, dsub):
+    x = normal((n, M * dsub), 100 + n)
+    q = random_codebook(M, k, dsub, 200 + n)
+    dt = np.uint8 if k <= 256 else np.uint16
+    pq = rb.Pq(None, q)
+    codes = pq.quantize_batch(x, dt)
+    want = oracle.quantize_batch(q, None, x, dt, n_threads=8)
+    assert np.array_equal(codes, want), f"{(codes != want).sum()} of {codes.size} codes differ"
+    rec = pq.reconstruct_batch(codes)
+    assert np.array_equal(rec.view(np.uint32), oracle.reconstruct_batch(q, None, want).view(np.uint32))
+
+
+def test_near_ties_duplicates_and_specials_bit_exact(oracle, algo):
+    M, k, dsub = 6, 256, 10
+    q = random_codebook(M, k, dsub, 5)
+    q[:, 17] = q[:, 3]      # exact duplicate centroids: first index must win
+    q[:, 200] = q[:, 100]
+    x = np.concatenate([near_tie_rows(q, 20_000, 6), np.zeros((3, M * dsub), F), -np.zeros((2, M * dsub), F),
+                        np.full((2, M * dsub), 1e-41, F),               # denormals
+                        np.full((2, M * dsub), 3.0, F)])               # all-equal rows
+    codes = rb.Pq(None, q).quantize_batch(x, np.uint8)
+    want = oracle.quantize_batch(q, None, x, np.uint8, n_threads=8)
+    assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ"
+
+
+def test_nan_and_inf_rank_like_ordered_float(oracle, algo):
+    M, k, dsub = 2, 32, 8
+    q = random_codebook(M, k, dsub, 9)
+    q[0, 0, 0] = np.nan
+    q[1, 5, 2] = np.inf
+    x = normal((500, M * dsub), 10)
+    x[7, 3] = np.nan
+    x[8, 9] = np.inf
+    x[9, :] = np.nan
+    x[10, 0] = -np.inf
+    x[11, :] = 1e30   # overflowing norms
+    codes = rb.Pq(None, q).quantize_batch(x, np.uint8)
+    want = oracle.quantize_batch(q, None, x, np.uint8)
+    assert np.array_equal(codes, want)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64, np.int32])
+def test_code_types_and_truncating_cast(oracle, dtype):
+    q = random_codebook(2, 300, 4, 31)
+    x = normal((2_000, 8), 32)
+    codes = rb.Pq(None, q).quantize_batch(x, dtype)   # k = 300 > u8: the batch path truncates (primitives.rs:100)
+    want = oracle.quantize_batch(q, None, x, np.dtype(dtype).type if np.dtype(dtype).kind == "u" else np.uint32)
+    mask = np.uint64(2 ** (8 * np.dtype(dtype).itemsize) - 1)
+    assert np.array_equal(codes.astype(np.uint64) & mask, want.astype(np.uint64) & mask)
+
+
+def test_strided_views_host_and_device(oracle, torch_cuda, algo):
+    torch = torch_cuda
+    M, k, dsub = 5, 64, 6
+    q = random_codebook(M, k, dsub, 41)
+    big = normal((4_000, 2 * M * dsub + 3), 42)
+    pq = rb.Pq(None, q)
+    views = {
+        "row_pitch": big[:, :M * dsub],                      # unit column stride, padded rows
+        "every_other_row": big[::2, 3:3 + M * dsub],
+        "fortran": np.asfortranarray(big[:, :M * dsub]),     # column-major: sequential-dot norms in the reference
+        "col_step": big[:, 0:2 * M * dsub:2],
+    }
+    for name, v in views.items():
+        want = oracle.quantize_batch(q, None, v, np.uint8)
+        assert np.array_equal(pq.quantize_batch(v, np.uint8), want), name
+        t = torch.from_numpy(big).cuda()
+        if name == "row_pitch":
+            tv = t[:, :M * dsub]
+        elif name == "every_other_row":
+            tv = t[::2, 3:3 + M * dsub]
+        elif name == "fortran":
+            tv = t[:, :M * dsub].t().contiguous().t()
+        else:
+            tv = t[:, 0:2 * M * dsub:2]
+        assert np.array_equal(pq.quantize_batch(tv, np.uint8).cpu().numpy(), want), name + " (device)"
+    # strided outputs: codes into a column-sliced buffer, reconstructions into a padded buffer
+    out = np.zeros((4_000, 2 * M), np.uint8)
+    pq.quantize_batch_into(views["row_pitch"], out[:, ::2])
+    want = oracle.quantize_batch(q, None, views["row_pitch"], np.uint8)
+    assert np.array_equal(out[:, ::2], want) and not out[:, 1::2].any()
+    rec = np.zeros((4_000, M * dsub + 5), F)
+    pq.reconstruct_batch_into(out[:, ::2], rec[:, 2:2 + M * dsub])
+    assert np.array_equal(rec[:, 2:2 + M * dsub], oracle.reconstruct_batch(q, None, want))
+    assert not rec[:, :2].any() and not rec[:, 2 + M * dsub:].any()
+    rec_t = np.zeros((M * dsub, 4_000), F)
+    pq.reconstruct_batch_into(want, rec_t.T)
+    assert np.array_equal(rec_t.T, oracle.reconstruct_batch(q, None, want))
+
+
+def test_empty_batch():
+    pq = rb.Pq(None, random_codebook(3, 16, 4, 1))
+    assert pq.quantize_batch(np.zeros((0, 12), F)).shape == (0, 3)
+    assert pq.reconstruct_batch(np.zeros((0, 3), np.uint8)).shape == (0, 12)
+
+
+def test_shape_mismatches_panic_like_the_reference():
+    pq = rb.Pq(None, random_codebook(3, 16, 4, 1))
+    with pytest.raises(rb.ReductivePanic):  # primitives.rs:74-78
+        pq.quantize_batch(np.zeros((5, 11), F))
+    with pytest.raises(rb.ReductivePanic):  # primitives.rs:80-87
+        pq.quantize_batch_into(np.zeros((5, 12), F), np.zeros((5, 4), np.uint8))
+    with pytest.raises(rb.ReductivePanic):  # primitives.rs:25-29
+        pq.quantize_vector(np.zeros((11,), F))
+    with pytest.raises(rb.ReductivePanic):  # primitives.rs:159-167
+        pq.reconstruct_batch_into(np.zeros((5, 3), np.uint8), np.zeros((5, 13), F))
+    with pytest.raises(IndexError):  # out-of-range code: ndarray index panic in the reference
+        pq.reconstruct_batch(np.full((5, 3), 16, np.uint8))
+    with pytest.raises(IndexError):
+        pq.reconstruct(np.array([0, 99, 0], np.uint8))
+
+
+def test_vector_paths_bit_exact(oracle):
+    M, k, dsub = 4, 128, 9
+    q = random_codebook(M, k, dsub, 51)
+    x = normal((64, M * dsub), 52)
+    r = orthonormal(M * dsub, 53)
+    for proj in (None, r):
+        pq = rb.Pq(proj, q)
+        for i in range(64):
+            want = oracle.quantize_vector(q, proj, x[i], np.uint8)
+            assert np.array_equal(pq.quantize_vector(x[i], np.uint8), want)
+            assert np.array_equal(pq.reconstruct(want).view(np.uint32), oracle.reconstruct(q, proj, want).view(np.uint32))
+    xs = normal((2 * M * dsub,), 54)[::2]   # strided vector view
+    assert np.array_equal(rb.Pq(None, q).quantize_vector(xs, np.uint8), oracle.quantize_vector(q, None, xs, np.uint8))
+
+
+@pytest.mark.parametrize("n,M,k,dsub", [(6_000, 10, 256, 30), (6_000, 30, 256, 10), (1_000, 4, 32, 80)])
+def test_projected_encode_decode_bit_exact(oracle, algo, n, M, k, dsub):
+    """Opq / GaussianOpq use: x.R before the argmin, R^T after the gather (pq.rs:276, 323-326).  d = 300/320 > kc
+    exercises the 256-block split of the reference GEMM."""
+    d = M * dsub
+    q, r, x = random_codebook(M, k, dsub, 61), orthonormal(d, 62), normal((n, d), 63)
+    pq = rb.Pq(r, q)
+    codes = pq.quantize_batch(x, np.uint8)
+    want = oracle.quantize_batch(q, r, x, np.uint8, n_threads=8)
+    assert np.array_equal(codes, want)
+    rec = pq.reconstruct_batch(codes)
+    want_rec = oracle.reconstruct_batch(q, r, want, n_threads=8)
+    assert np.array_equal(rec.view(np.uint32), want_rec.view(np.uint32))
+    # north_star's stated tolerance for the rotated reconstruction, for the record
+    assert np.abs(rec - want_rec).max() <= 1e-5 * np.abs(want_rec).max()
+
+
+# ---- k-means / training ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,M,bits,dsub,iters", [(10_000, 10, 8, 30, 10), (20_000, 12, 8, 8, 6), (3_000, 5, 4, 6, 8)])
+def test_train_pq_matches_oracle_from_identical_initial_centroids(oracle, algo, n, M, bits, dsub, iters):
+    x = normal((n, M * dsub), 71)
+    init = rows_as_initial_centroids(x, M, 1 << bits, 72)
+    pq, loss = rb.Pq.train_pq_using(M, bits, iters, 1, x, None, initial_centroids=init, return_loss=True)
+    want_q, want_loss = oracle.train_pq(x, M, bits, iters, 1, init, n_threads=8)
+    got = pq.subquantizers()
+    for m in range(M):
+        rel = np.linalg.norm(got[m] - want_q[m]) / np.linalg.norm(want_q[m])
+        assert rel <= 1e-4, f"subquantizer {m}: relative error {rel}"
+    assert np.allclose(loss, want_loss, rtol=1e-3)
+
+
+def test_single_kmeans_iteration_is_tight(oracle, torch_cuda):
+    """One Lloyd step has no chaotic amplification: identical assignments, sums equal to summation-order error."""
+    torch = torch_cuda
+    x = normal((50_000, 8), 81)
+    init = rows_as_initial_centroids(x, 1, 256, 82)[0, 0]
+    want_c, want_loss = oracle.kmeans_iteration(x, init)
+    cen = torch.from_numpy(init.copy()).cuda()
+    loss = rb.kmeans_iteration(torch.from_numpy(x).cuda(), cen)
+    assert np.abs(cen.cpu().numpy() - want_c).max() <= 2e-6 * np.abs(want_c).max()
+    assert abs(loss - want_loss) <= 1e-5 * want_loss
+
+
+def test_empty_clusters_stay_zero(oracle, torch_cuda):  # kmeans.rs:181,194
+    torch = torch_cuda
+    x = normal((400, 4), 91)
+    cen0 = np.concatenate([x[:6], np.full((2, 4), 1e3, F)])   # two centroids nobody is assigned to
+    want_c, _ = oracle.kmeans_iteration(x, cen0)
+    cen = torch.from_numpy(cen0.copy()).cuda()
+    rb.kmeans_iteration(torch.from_numpy(x).cuda(), cen)
+    got = cen.cpu().numpy()
+    assert not got[6:].any() and not want_c[6:].any()
+    assert np.allclose(got, want_c, rtol=1e-5, atol=1e-6)
+
+
+def test_multi_attempt_training_picks_lowest_loss(oracle):
+    x = normal((2_000, 8), 95)
+    init = rows_as_initial_centroids(x, 2, 8, 96, n_attempts=3)
+    pq, loss = rb.Pq.train_pq_using(2, 3, 4, 3, x, None, initial_centroids=init, return_loss=True)
+    want_q, want_loss = oracle.train_pq(x, 2, 3, 4, 3, init)
+    assert np.allclose(loss, want_loss, rtol=1e-3)
+    assert np.linalg.norm(pq.subquantizers() - want_q) / np.linalg.norm(want_q) <= 1e-4
+
+
+def test_train_validation_errors():
+    x = normal((256, 20), 1)
+    with pytest.raises(rb.IncorrectNSubquantizerBits):
+        rb.Pq.train_pq_using(10, 9, 10, 1, x, np.random.default_rng(0))
+    with pytest.raises(rb.IncorrectNumberSubquantizers):
+        rb.Pq.train_pq_using(3, 7, 10, 1, x, np.random.default_rng(0))
+    with pytest.raises(rb.ReductivePanic):  # k == n: RandomInstanceCentroids asserts k < n (kmeans.rs:62-67)
+        rb.Pq.train_pq_using(10, 8, 10, 1, x, np.random.default_rng(0))
+
+
+# ---- the reference's statistical end-to-end tests ------------------------------------------------------
+def _avg_euclidean_loss(x, pq):  # pq.rs:365-376
+    rec = pq.reconstruct_batch(pq.quantize_batch(x, np.uint8))
+    return float(np.mean(np.sqrt(((x - rec) ** 2).sum(1))))
+
+
+def test_quantize_with_pq():  # pq.rs:431-440
+    rng = np.random.default_rng(42)
+    x = rng.random((256, 20), F)
+    assert _avg_euclidean_loss(x, rb.Pq.train_pq_using(10, 7, 10, 1, x, rng)) < 0.08
+
+
+def test_quantize_with_opq():  # opq.rs:330-339
+    rng = np.random.default_rng(42)
+    x = rng.random((256, 20), F)
+    pq = rb.Opq.train_pq_using(10, 7, 10, 1, x, rng)
+    assert pq.projection() is not None and _avg_euclidean_loss(x, pq) < 0.1
+
+
+def test_quantize_with_gaussian_opq():  # gaussian_opq.rs:99-108
+    rng = np.random.default_rng(42)
+    x = rng.random((256, 20), F)
+    pq = rb.GaussianOpq.train_pq_using(10, 7, 10, 1, x, rng)
+    assert pq.projection() is not None and _avg_euclidean_loss(x, pq) < 0.12
+
+
+def test_k_means_3():  # kmeans.rs:459-479
+    rng = np.random.default_rng(3)
+    centers = np.array([[0., 0.], [1., 0.], [1., 1.]], F)
+    x = np.concatenate([c + rng.normal(0, 0.01, (11, 2)).astype(F) for c in centers]).astype(F)
+
+    class OnePerBlob:
+        def initial_centroids(self, data, k):
+            return data[[0, 11, 22]].clone()
+
+    cen, _ = rb.KMeans.k_means(x, 3, OnePerBlob(), rb.NIterationsCondition(10))
+    assert sorted(map(tuple, np.rint(cen).astype(int).tolist())) == [(0, 0), (1, 0), (1, 1)]
