@@ -74,6 +74,11 @@ uint64_t rb_kernel_launch_count(void);
 /* Process-wide default for RB_ENCODE_AUTO resolution (tests force each path). */
 rb_status rb_set_encode_algo(int algo);
 
+/* Centroid-update summation order of the k-means entry points (process-wide).  ordered != 0 (default):
+ * rows of a cluster are added sequentially in row order exactly like kmeans.rs:185-189, so sums are
+ * bit-identical to the reference's on one GPU; 0: shared-memory atomics, order unspecified. */
+rb_status rb_set_kmeans_update(int ordered);
+
 /* ---- Pq construction and accessors ----------------------------------------------------------- */
 
 /* Pq::new(projection, quantizers)  pq.rs:38-61.  quantizers: HOST [M,k,dsub] contiguous;

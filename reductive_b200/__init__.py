@@ -7,7 +7,7 @@ is a NoDeviceError at the first compute call.
 from ._cabi import (  # noqa: F401
     ENCODE_AUTO, ENCODE_EXACT, ENCODE_TENSOR, ConstructRng, CudaError, IncorrectNAttempts, IncorrectNIterations,
     IncorrectNSubquantizerBits, IncorrectNumberSubquantizers, NoDeviceError, NSubquantizersOutsideRange,
-    ReductiveError, ReductivePanic, kernel_launch_count, set_encode_algo,
+    ReductiveError, ReductivePanic, kernel_launch_count, set_encode_algo, set_kmeans_update,
 )
 from .kmeans import (  # noqa: F401
     KMeans, NIterationsCondition, RandomInstanceCentroids, kmeans_iteration, kmeans_with_centroids,

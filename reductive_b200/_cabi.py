@@ -34,6 +34,7 @@ ENCODE_AUTO, ENCODE_EXACT, ENCODE_TENSOR = 0, 1, 2
 # every symbol include/reductive_b200.h declares (tests check the library exports each one)
 EXPORTED_SYMBOLS = [
     "rb_last_error_message", "rb_abi_version", "rb_kernel_launch_count", "rb_set_encode_algo",
+    "rb_set_kmeans_update",
     "rb_pq_create", "rb_pq_destroy", "rb_pq_quantized_len", "rb_pq_reconstructed_len",
     "rb_pq_n_quantizer_centroids", "rb_pq_has_projection", "rb_pq_subquantizers", "rb_pq_projection",
     "rb_pq_quantize_batch", "rb_pq_quantize_vector", "rb_pq_reconstruct_batch", "rb_pq_reconstruct",
@@ -99,6 +100,7 @@ def _load() -> C.CDLL:
     lib.rb_abi_version.restype = C.c_int
     lib.rb_kernel_launch_count.restype = C.c_uint64
     lib.rb_set_encode_algo.argtypes = [C.c_int]
+    lib.rb_set_kmeans_update.argtypes = [C.c_int]
     lib.rb_pq_create.argtypes = [fp, sz, sz, sz, fp, C.POINTER(vp)]
     lib.rb_pq_destroy.argtypes = [vp]
     lib.rb_pq_destroy.restype = None
@@ -155,3 +157,8 @@ def kernel_launch_count() -> int:
 
 def set_encode_algo(algo: int) -> None:
     check(lib.rb_set_encode_algo(algo))
+
+
+def set_kmeans_update(ordered: bool) -> None:
+    """ordered=True (default): reference summation order, bit-exact sums on one GPU; False: atomics."""
+    check(lib.rb_set_kmeans_update(1 if ordered else 0))

@@ -15,6 +15,7 @@ namespace rb {
 
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_encode_algo{RB_ENCODE_AUTO};
+static std::atomic<int> g_kmeans_ordered{1};
 static thread_local char t_err[512] = "";
 
 void set_error(const char *fmt, ...)
@@ -384,6 +385,12 @@ rb_status rb_set_encode_algo(int algo)
     return RB_OK;
 }
 
+rb_status rb_set_kmeans_update(int ordered)
+{
+    g_kmeans_ordered.store(ordered ? 1 : 0);
+    return RB_OK;
+}
+
 rb_status rb_pq_create(const float *quantizers, size_t M, size_t k, size_t dsub, const float *projection,
                        rb_pq **out)
 {
@@ -617,7 +624,8 @@ rb_status rb_kmeans_assign_accumulate(const float *x, size_t n_local, ptrdiff_t 
     rb_status s = encode_device(cb, &tc, x, n_local, ldx, 0, codes.p, width, (ptrdiff_t)M, 1, st);  // kmeans.rs:319
     if (s == RB_OK)
         s = launch_kmeans_accumulate(x, n_local, ldx, width == 1 ? codes.as<uint8_t>() : nullptr,
-                                     width == 4 ? codes.as<uint32_t>() : nullptr, M, k, dsub, packed, st);
+                                     width == 4 ? codes.as<uint32_t>() : nullptr, M, k, dsub, packed,
+                                     g_kmeans_ordered.load(), st);
     tc.release_async(st);
     return s;
 }

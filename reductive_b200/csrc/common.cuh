@@ -185,7 +185,7 @@ rb_status launch_project(const float *x, size_t n, size_t d, ptrdiff_t rsx, ptrd
 // kmeans.cu
 rb_status launch_kmeans_accumulate(const float *x, size_t n, ptrdiff_t ldx, const uint8_t *codes8,
                                    const uint32_t *codes32, size_t M, size_t k, size_t dsub, float *packed,
-                                   cudaStream_t stream);
+                                   int ordered, cudaStream_t stream);
 rb_status launch_kmeans_finalize(const float *packed, size_t M, size_t k, size_t dsub, uint64_t n_total,
                                  float *centroids, float *loss, cudaStream_t stream);
 

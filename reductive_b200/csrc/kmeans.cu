@@ -13,8 +13,18 @@
 //   count`, kmeans.rs:195), leaves empty clusters at zero (kmeans.rs:181,194), and evaluates
 //   sum ||x - c_a||^2 = sum ||x||^2 - 2 sum_j c_j.S_j + sum_j n_j ||c_j||^2 in FP64.
 //
-// Parity: the reference adds rows sequentially in row order; this adds them in parallel, so sums agree
-// to FP32 summation-order error (tests bound trained centroids at 1e-4 relative, as north_star states).
+// Two accumulate paths produce the same packed layout:
+//   ordered (default, k <= 1024): reproduces the reference's summation ORDER.  kmeans.rs:185-189 adds the rows
+//     of a cluster sequentially in increasing row order in f32; k-means is chaotic (one last-bit difference in
+//     a centroid flips a near-tie assignment, which moves two centroids by 1/count), so only the same order
+//     keeps trained centroids equal to the oracle's.  Implemented as a stable counting sort of the row indices
+//     by code (per-chunk histograms -> scan -> stable warp-synchronous scatter) followed by one sequential
+//     f32 chain per (subquantizer, cluster, component) — M*k*dsub independent chains, 8 gathers in flight each.
+//     Result: sums, hence trained centroids, are BIT-IDENTICAL to the oracle on one GPU.
+//   atomic: shared-memory atomics, summation order unspecified (FP32 order-of-summation error ~1e-7 relative);
+//     used for k > 1024.
+// Across ranks (data-parallel k-means) the all-reduce adds per-rank partial sums, which is not the
+// single sequential chain either: multi-GPU training is tolerance-level (1e-4), single-GPU is bit-exact.
 // Counts follow the reference's f32 `+= 1.0` (exact to 2^24 per cluster, kmeans.rs:188).
 #include "common.cuh"
 
@@ -97,6 +107,143 @@ accumulate_kernel(const float *__restrict__ x, long long n, long long ldx, const
     }
 }
 
+
+// ---- ordered path ---------------------------------------------------------------------------------------
+constexpr int kSortWarps = 4;  // warps per block; each warp owns one (row chunk, subquantizer) pair
+
+// Pass 1: per (chunk, m) histogram of codes.  cnt layout [chunk][m][k].
+template <typename CodeT>
+__global__ void __launch_bounds__(kSortWarps * 32)
+sort_hist_kernel(const CodeT *__restrict__ codes, long long n, int M, int k, long long rows_per_chunk, int n_chunks,
+                 unsigned *__restrict__ cnt)
+{
+    extern __shared__ unsigned sh[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long pair = (long long)blockIdx.x * kSortWarps + warp;
+    unsigned *h = sh + (size_t)warp * k;
+    for (int i = lane; i < k; i += 32) h[i] = 0;
+    __syncwarp();
+    if (pair < (long long)n_chunks * M) {
+        const int chunk = (int)(pair / M), m = (int)(pair % M);
+        const long long r0 = (long long)chunk * rows_per_chunk, r1 = min(n, r0 + rows_per_chunk);
+        for (long long row = r0 + lane; row < r1; row += 32) atomicAdd(h + (unsigned)codes[row * M + m], 1u);
+        __syncwarp();
+        unsigned *dst = cnt + (size_t)pair * k;
+        for (int i = lane; i < k; i += 32) dst[i] = h[i];
+    }
+}
+
+// Pass 2: for every (m, j): exclusive scan over chunks (in place: cnt becomes the chunk's start offset inside
+// the cluster's list) and the cluster total; then per m an exclusive scan over j gives the list bases.
+__global__ void sort_scan_kernel(unsigned *__restrict__ cnt, int M, int k, int n_chunks, unsigned *__restrict__ total,
+                                 unsigned *__restrict__ base)
+{
+    const int m = blockIdx.x;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        unsigned run = 0;
+        for (int c = 0; c < n_chunks; c++) {
+            unsigned *p = cnt + ((size_t)c * M + m) * k + j;
+            const unsigned v = *p;
+            *p = run;
+            run += v;
+        }
+        total[(size_t)m * k + j] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int j = 0; j < k; j++) {
+            base[(size_t)m * k + j] = run;
+            run += total[(size_t)m * k + j];
+        }
+    }
+}
+
+// Pass 3: stable scatter of row indices.  list layout [m][n]; cluster j of subquantizer m occupies
+// list[m][base[m][j] .. + total[m][j]) in increasing row order.
+template <typename CodeT>
+__global__ void __launch_bounds__(kSortWarps * 32)
+sort_scatter_kernel(const CodeT *__restrict__ codes, long long n, int M, int k, long long rows_per_chunk, int n_chunks,
+                    const unsigned *__restrict__ off, const unsigned *__restrict__ base, unsigned *__restrict__ list)
+{
+    extern __shared__ unsigned sh[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long pair = (long long)blockIdx.x * kSortWarps + warp;
+    if (pair >= (long long)n_chunks * M) return;
+    const int chunk = (int)(pair / M), m = (int)(pair % M);
+    unsigned *pos = sh + (size_t)warp * k;  // next free slot of every cluster, for this chunk
+    for (int i = lane; i < k; i += 32) pos[i] = base[(size_t)m * k + i] + off[(size_t)pair * k + i];
+    __syncwarp();
+    const long long r0 = (long long)chunk * rows_per_chunk, r1 = min(n, r0 + rows_per_chunk);
+    unsigned *lm = list + (size_t)m * n;
+    for (long long rb = r0; rb < r1; rb += 32) {
+        const long long row = rb + lane;
+        const bool live = row < r1;
+        const unsigned code = live ? (unsigned)codes[row * M + m] : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, code);  // lanes (= consecutive rows) with my code
+        if (live) {
+            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            lm[pos[code] + rank] = (unsigned)row;
+        }
+        __syncwarp();
+        if (live && (peers >> lane) == 1u) pos[code] += __popc(peers);  // highest lane of the group advances
+        __syncwarp();
+    }
+}
+
+// Pass 4: one sequential f32 chain per (m, j, t) in row order (kmeans.rs:185-189), 8 gathers in flight.
+__global__ void __launch_bounds__(256)
+ordered_sum_kernel(const float *__restrict__ x, long long ldx, long long n, int M, int k, int dsub,
+                   const unsigned *__restrict__ list, const unsigned *__restrict__ total,
+                   const unsigned *__restrict__ base, float *__restrict__ packed)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long chains = (long long)M * k * dsub;
+    double sq = 0.0;
+    int m = 0;
+    if (tid < chains) {
+        const int t = (int)(tid % dsub);
+        const long long mj = tid / dsub;
+        m = (int)(mj / k);
+        const unsigned cnt = total[mj];
+        const unsigned *l = list + (size_t)m * n + base[mj];
+        const float *xc = x + (long long)m * dsub + t;
+        float acc = 0.f;
+        unsigned i = 0;
+        for (; i + 8 <= cnt; i += 8) {
+            unsigned r[8];
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) r[u] = __ldg(l + i + u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldg(xc + (long long)r[u] * ldx);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                acc = __fadd_rn(acc, v[u]);
+                sq += (double)v[u] * (double)v[u];
+            }
+        }
+        for (; i < cnt; i++) {
+            const float v = __ldg(xc + (long long)__ldg(l + i) * ldx);
+            acc = __fadd_rn(acc, v);
+            sq += (double)v * (double)v;
+        }
+        packed[tid] = acc;
+        if (t == 0) packed[chains + mj] = (float)cnt;
+    }
+    // squared-norm partials: threads of one warp may straddle two subquantizers only when k*dsub % 32 != 0;
+    // use per-thread atomics in that (rare) case, a warp reduction otherwise.
+    float *gsq = packed + chains + (long long)M * k;
+    const bool uniform = ((long long)k * dsub) % 32 == 0;
+    if (uniform) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        if ((threadIdx.x & 31) == 0 && tid < chains) atomicAdd(gsq + m, (float)sq);
+    } else if (tid < chains) {
+        atomicAdd(gsq + m, (float)sq);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 finalize_kernel(const float *__restrict__ packed, int M, int k, int dsub, double inv_len, float *__restrict__ centroids,
                 float *__restrict__ loss)
@@ -159,14 +306,60 @@ rb_status launch_acc_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT *cod
     return RB_OK;
 }
 
+
+template <typename CodeT>
+rb_status launch_ordered_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT *codes, size_t M, size_t k, size_t dsub,
+                           float *packed, cudaStream_t stream)
+{
+    // chunks: about 2 waves of warps over the GPU, at least 256 rows per chunk
+    size_t n_chunks = ceil_div((size_t)148 * 64, M);
+    size_t rows_per_chunk = ceil_div(n, n_chunks);
+    if (rows_per_chunk < 256) rows_per_chunk = 256;
+    n_chunks = ceil_div(n, rows_per_chunk);
+    const size_t pairs = n_chunks * M;
+    unsigned *cnt = nullptr, *total = nullptr, *base = nullptr, *list = nullptr;
+    RB_CUDA_TRY(cudaMallocAsync(&cnt, pairs * k * sizeof(unsigned), stream));
+    RB_CUDA_TRY(cudaMallocAsync(&total, M * k * sizeof(unsigned), stream));
+    RB_CUDA_TRY(cudaMallocAsync(&base, M * k * sizeof(unsigned), stream));
+    RB_CUDA_TRY(cudaMallocAsync(&list, M * n * sizeof(unsigned), stream));
+    const size_t smem = (size_t)kSortWarps * k * sizeof(unsigned);
+    const unsigned blocks = (unsigned)ceil_div(pairs, kSortWarps);
+    rb_status st = RB_OK;
+    auto body = [&]() -> rb_status {
+        sort_hist_kernel<CodeT><<<blocks, kSortWarps * 32, smem, stream>>>(codes, (long long)n, (int)M, (int)k,
+                                                                          (long long)rows_per_chunk, (int)n_chunks, cnt);
+        RB_LAUNCH_CHECK();
+        sort_scan_kernel<<<(unsigned)M, 256, 0, stream>>>(cnt, (int)M, (int)k, (int)n_chunks, total, base);
+        RB_LAUNCH_CHECK();
+        sort_scatter_kernel<CodeT><<<blocks, kSortWarps * 32, smem, stream>>>(
+            codes, (long long)n, (int)M, (int)k, (long long)rows_per_chunk, (int)n_chunks, cnt, base, list);
+        RB_LAUNCH_CHECK();
+        const size_t chains = M * k * dsub;
+        ordered_sum_kernel<<<(unsigned)ceil_div(chains, 256), 256, 0, stream>>>(
+            x, (long long)ldx, (long long)n, (int)M, (int)k, (int)dsub, list, total, base, packed);
+        RB_LAUNCH_CHECK();
+        return RB_OK;
+    };
+    st = body();
+    cudaFreeAsync(cnt, stream);
+    cudaFreeAsync(total, stream);
+    cudaFreeAsync(base, stream);
+    cudaFreeAsync(list, stream);
+    return st;
+}
+
 }  // namespace
 
 rb_status launch_kmeans_accumulate(const float *x, size_t n, ptrdiff_t ldx, const uint8_t *codes8,
                                    const uint32_t *codes32, size_t M, size_t k, size_t dsub, float *packed,
-                                   cudaStream_t stream)
+                                   int ordered, cudaStream_t stream)
 {
     RB_CUDA_TRY(cudaMemsetAsync(packed, 0, rb_kmeans_packed_len(M, k, dsub) * sizeof(float), stream));
     if (n == 0) return RB_OK;
+    if (ordered && k <= 1024 && n < ((size_t)1 << 32)) {
+        if (codes8) return launch_ordered_t<uint8_t>(x, n, ldx, codes8, M, k, dsub, packed, stream);
+        return launch_ordered_t<uint32_t>(x, n, ldx, codes32, M, k, dsub, packed, stream);
+    }
     if (codes8) return launch_acc_t<uint8_t>(x, n, ldx, codes8, M, k, dsub, packed, stream);
     return launch_acc_t<uint32_t>(x, n, ldx, codes32, M, k, dsub, packed, stream);
 }

@@ -253,16 +253,35 @@ def test_projected_encode_decode_bit_exact(oracle, algo, n, M, k, dsub):
 
 # ---- k-means / training ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,M,bits,dsub,iters", [(10_000, 10, 8, 30, 10), (20_000, 12, 8, 8, 6), (3_000, 5, 4, 6, 8)])
-def test_train_pq_matches_oracle_from_identical_initial_centroids(oracle, algo, n, M, bits, dsub, iters):
+def test_train_pq_bit_exact_from_identical_initial_centroids(oracle, algo, n, M, bits, dsub, iters):
+    """Single GPU, reference-order centroid update: assignments are bit-exact and the per-cluster sums are added in
+    the reference's row order, so the trained codebook is IDENTICAL to the oracle's (north_star asks <= 1e-4)."""
     x = normal((n, M * dsub), 71)
     init = rows_as_initial_centroids(x, M, 1 << bits, 72)
     pq, loss = rb.Pq.train_pq_using(M, bits, iters, 1, x, None, initial_centroids=init, return_loss=True)
     want_q, want_loss = oracle.train_pq(x, M, bits, iters, 1, init, n_threads=8)
     got = pq.subquantizers()
+    assert np.array_equal(got.view(np.uint32), want_q.view(np.uint32)), \
+        f"max rel err {np.abs(got - want_q).max() / np.abs(want_q).max()}"
+    assert np.allclose(loss, want_loss, rtol=1e-3)
+
+
+def test_train_pq_atomic_update_within_tolerance(oracle):
+    """The unordered (shared-memory atomics) update differs from the reference by summation order only; with
+    ~1000 rows per cluster the trained codebook stays within north_star's 1e-4 relative."""
+    n, M, bits, dsub, iters = 60_000, 6, 6, 8, 5
+    x = normal((n, M * dsub), 73)
+    init = rows_as_initial_centroids(x, M, 1 << bits, 74)
+    rb.set_kmeans_update(False)
+    try:
+        pq = rb.Pq.train_pq_using(M, bits, iters, 1, x, None, initial_centroids=init)
+    finally:
+        rb.set_kmeans_update(True)
+    want_q, _ = oracle.train_pq(x, M, bits, iters, 1, init, n_threads=8)
+    got = pq.subquantizers()
     for m in range(M):
         rel = np.linalg.norm(got[m] - want_q[m]) / np.linalg.norm(want_q[m])
         assert rel <= 1e-4, f"subquantizer {m}: relative error {rel}"
-    assert np.allclose(loss, want_loss, rtol=1e-3)
 
 
 def test_single_kmeans_iteration_is_tight(oracle, torch_cuda):
@@ -273,8 +292,8 @@ def test_single_kmeans_iteration_is_tight(oracle, torch_cuda):
     want_c, want_loss = oracle.kmeans_iteration(x, init)
     cen = torch.from_numpy(init.copy()).cuda()
     loss = rb.kmeans_iteration(torch.from_numpy(x).cuda(), cen)
-    assert np.abs(cen.cpu().numpy() - want_c).max() <= 2e-6 * np.abs(want_c).max()
-    assert abs(loss - want_loss) <= 1e-5 * want_loss
+    assert np.array_equal(cen.cpu().numpy().view(np.uint32), want_c.view(np.uint32))
+    assert abs(loss - want_loss) <= 1e-4 * want_loss
 
 
 def test_empty_clusters_stay_zero(oracle, torch_cuda):  # kmeans.rs:181,194
@@ -286,7 +305,7 @@ def test_empty_clusters_stay_zero(oracle, torch_cuda):  # kmeans.rs:181,194
     rb.kmeans_iteration(torch.from_numpy(x).cuda(), cen)
     got = cen.cpu().numpy()
     assert not got[6:].any() and not want_c[6:].any()
-    assert np.allclose(got, want_c, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(got.view(np.uint32), want_c.view(np.uint32))
 
 
 def test_multi_attempt_training_picks_lowest_loss(oracle):
