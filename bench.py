@@ -209,6 +209,55 @@ def run_ours(args) -> None:
     e2e_value = world * e2e_rows / float(te.item())
     e2e_ok = bool(torch.equal(ch.to(dev), codes[:e2e_rows]))
 
+    # ---- secondary measurements (same JSON line, "extra"): reconstruct_batch and Pq k-means sec/iter ------
+    extra = {}
+    rec = torch.empty((N_ROWS, D), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        pq.reconstruct_batch_into(codes, rec)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(stream)
+    for _ in range(args.steps):
+        pq.reconstruct_batch_into(codes, rec)
+    r1.record(stream)
+    barrier()
+    tr = torch.tensor([r0.elapsed_time(r1) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+    rec_ms = float(tr.item())
+    rec_gbs = N_ROWS * (M + 4 * D) / (rec_ms * 1e-3) / 1e9
+    extra["reconstruct_batch"] = {
+        "workload": "C2 decode: 2M x 30 u8 codes -> 2M x 300 f32", "ms": rec_ms,
+        "vectors_per_s": world * N_ROWS / (rec_ms * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": rec_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": rec_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_vector": M + 4 * D}}
+    del rec
+    # C3: Pq k-means 1M x 768, 96 x 256, rows sharded over the ranks (strong scaling), one all-reduce per iteration
+    from reductive_b200.dist import kmeans_data_parallel, shard_rows
+
+    n3, M3, dsub3, iters3 = 1_000_000, 96, 8, 5
+    lo, hi = shard_rows(n3, rank, world)
+    g3 = torch.Generator(device=dev)
+    g3.manual_seed(77 + rank)
+    x3 = torch.randn((hi - lo, M3 * dsub3), generator=g3, device=dev, dtype=torch.float32)
+    gi = torch.Generator(device=dev)
+    gi.manual_seed(5)
+    cen3 = torch.randn((M3, K_CENTROIDS, dsub3), generator=gi, device=dev, dtype=torch.float32)
+    kmeans_data_parallel(x3, n3, cen3, 2)
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(stream)
+    kmeans_data_parallel(x3, n3, cen3, iters3)
+    k1.record(stream)
+    barrier()
+    tk = torch.tensor([k0.elapsed_time(k1) / iters3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+    extra["pq_kmeans"] = {"workload": f"C3: 1M x 768 f32, 96 x 256 centroids, rows sharded over {world} GPU(s)",
+                          "sec_per_iter": float(tk.item()) * 1e-3, "iters_timed": iters3,
+                          "allreduce_bytes_per_iter": 4 * (M3 * K_CENTROIDS * (dsub3 + 1) + M3) if world > 1 else 0}
+    del x3
+
     if rank == 0:
         # roofline of the dominant kernel (the encode kernel is the whole step): algorithmic bytes per vector
         # = 4*d + M, against the measured HBM copy bandwidth — at the measured peaks the HBM bound
@@ -252,7 +301,7 @@ def run_ours(args) -> None:
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_rows * D * 4,
                     "d2h_bytes_per_step": e2e_rows * M, "steps": e2e_steps, "codes_match_device_path": e2e_ok},
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra,
         }))
     if world > 1:
         dist.barrier()

@@ -263,7 +263,9 @@ static rb_status quantize_batch_host(const rb_pq *pq, const float *x, size_t n, 
         cudaStream_t st = pipe.st[slot];
         RB_TRY(drain(slot));
         float *xd = xin[slot].as<float>();
-        if (in2d) {
+        if (in2d && rs == (ptrdiff_t)d) {  // contiguous: one linear DMA (2-D copies of 1.2 KB rows run at ~1/5 speed)
+            RB_CUDA_TRY(cudaMemcpyAsync(xd, x + (ptrdiff_t)r0 * rs, rows * d * sizeof(float), cudaMemcpyHostToDevice, st));
+        } else if (in2d) {
             RB_CUDA_TRY(cudaMemcpy2DAsync(xd, d * sizeof(float), x + (ptrdiff_t)r0 * rs, (size_t)rs * sizeof(float),
                                           d * sizeof(float), rows, cudaMemcpyHostToDevice, st));
         } else {
@@ -281,7 +283,10 @@ static rb_status quantize_batch_host(const rb_pq *pq, const float *x, size_t n, 
         }
         RB_TRY(encode_device(pq->cb(), &pq->tc, src, rows, (ptrdiff_t)d, seq_norm, cout[slot].p, code_width,
                              (ptrdiff_t)M, 1, st));
-        if (out2d) {
+        if (out2d && crs == (ptrdiff_t)M) {
+            RB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char *>(codes) + (ptrdiff_t)r0 * crs * code_width, cout[slot].p,
+                                        rows * M * code_width, cudaMemcpyDeviceToHost, st));
+        } else if (out2d) {
             RB_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<char *>(codes) + (ptrdiff_t)r0 * crs * code_width,
                                           (size_t)crs * code_width, cout[slot].p, M * code_width, M * code_width, rows,
                                           cudaMemcpyDeviceToHost, st));
@@ -335,7 +340,9 @@ static rb_status reconstruct_batch_host(const rb_pq *pq, const void *codes, int 
         cudaStream_t st = pipe.st[slot];
         RB_TRY(drain(slot));
         const char *csrc = reinterpret_cast<const char *>(codes) + (ptrdiff_t)r0 * crs * code_width;
-        if (in2d) {
+        if (in2d && crs == (ptrdiff_t)M) {
+            RB_CUDA_TRY(cudaMemcpyAsync(cin[slot].p, csrc, rows * M * code_width, cudaMemcpyHostToDevice, st));
+        } else if (in2d) {
             RB_CUDA_TRY(cudaMemcpy2DAsync(cin[slot].p, M * code_width, csrc, (size_t)crs * code_width, M * code_width,
                                           rows, cudaMemcpyHostToDevice, st));
         } else {
@@ -347,7 +354,10 @@ static rb_status reconstruct_batch_host(const rb_pq *pq, const void *codes, int 
         }
         RB_TRY(reconstruct_batch_device(pq, cin[slot].p, code_width, rows, (ptrdiff_t)M, 1, yout[slot].as<float>(),
                                         (ptrdiff_t)d, 1, flag.as<int>(), st));
-        if (out2d) {
+        if (out2d && ors == (ptrdiff_t)d) {
+            RB_CUDA_TRY(cudaMemcpyAsync(out + (ptrdiff_t)r0 * ors, yout[slot].p, rows * d * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st));
+        } else if (out2d) {
             RB_CUDA_TRY(cudaMemcpy2DAsync(out + (ptrdiff_t)r0 * ors, (size_t)ors * sizeof(float), yout[slot].p,
                                           d * sizeof(float), d * sizeof(float), rows, cudaMemcpyDeviceToHost, st));
         } else {
@@ -659,7 +669,9 @@ rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t rs, 
     ptrdiff_t ldx = rs;
     if (mem_kind == RB_MEM_HOST) {
         RB_TRY(xbuf.alloc(n * d * sizeof(float), st));
-        if (cs == 1 && rs >= (ptrdiff_t)d) {
+        if (cs == 1 && rs == (ptrdiff_t)d) {
+            RB_CUDA_TRY(cudaMemcpyAsync(xbuf.p, instances, n * d * sizeof(float), cudaMemcpyHostToDevice, st));
+        } else if (cs == 1 && rs >= (ptrdiff_t)d) {
             RB_CUDA_TRY(cudaMemcpy2DAsync(xbuf.p, d * sizeof(float), instances, (size_t)rs * sizeof(float),
                                           d * sizeof(float), n, cudaMemcpyHostToDevice, st));
         } else {
