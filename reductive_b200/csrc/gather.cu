@@ -20,7 +20,8 @@ namespace rb {
 
 namespace {
 
-constexpr int kGatherThreads = 256;
+constexpr int kGatherThreads = 512;
+constexpr int kUnroll = 8;
 
 template <int PW>
 struct VecT;
@@ -45,7 +46,7 @@ __device__ __forceinline__ void store_streaming(float *dst, typename VecT<PW>::t
 
 // grid.x = row strips, grid.y = column groups.
 //   piece p (local to the group) -> (m_local = p / ppsq, t = (p % ppsq) * PW), ppsq = dsub / PW.
-template <int PW, bool SMEM_CB>
+template <int PW, bool SMEM_CB, int CW>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, const void *__restrict__ codes,
               int code_width, long long n, long long crs, long long ccs, float *__restrict__ out, long long ldo,
@@ -91,30 +92,36 @@ gather_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, cons
         const long long out_col = (long long)(m0 + ml) * dsub + t;
         const float *csrc = cbase + (size_t)ml * k * dsub + t;
 
-        // 4 independent rows in flight per thread
-        for (long long row = r0 + rl; row < r1; row += 4LL * rows_par) {
-            V v[4];
-            bool live[4];
+        // kUnroll independent rows in flight per thread, in three branch-free phases so that the code loads of
+        // all rows are issued back to back (a data-dependent branch between them serialises the round trips).
+        for (long long row = r0 + rl; row < r1; row += (long long)kUnroll * rows_par) {
+            unsigned code[kUnroll];
+            V v[kUnroll];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const long long rr = row + (long long)u * rows_par;
-                live[u] = rr < r1;
-                if (live[u]) {
-                    const unsigned long long code = load_code(codes, code_width, rr * crs + code_col);
-                    if (code >= (unsigned long long)k) {
-                        bad = true;
-                        live[u] = false;
-                    } else if constexpr (SMEM_CB) {
-                        v[u] = *reinterpret_cast<const V *>(csrc + (size_t)code * dsub);
-                    } else {
-                        v[u] = __ldg(reinterpret_cast<const V *>(csrc + (size_t)code * dsub));
-                    }
+            for (int u = 0; u < kUnroll; u++) {
+                const long long rr = min(row + (long long)u * rows_par, r1 - 1);  // clamp: re-reads the last row
+                if constexpr (CW == 1) {  // u8 codes (the production shape): no width dispatch inside the loop
+                    code[u] = reinterpret_cast<const uint8_t *>(codes)[rr * crs + code_col];
+                } else {
+                    code[u] = (unsigned)min(load_code(codes, code_width, rr * crs + code_col),
+                                            (unsigned long long)0xffffffffu);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (live[u]) {
-                    float *dst = out + (row + (long long)u * rows_par) * ldo + out_col;
+            for (int u = 0; u < kUnroll; u++) {
+                bad |= code[u] >= (unsigned)k;
+                const unsigned c = min(code[u], (unsigned)(k - 1));
+                if constexpr (SMEM_CB) {
+                    v[u] = *reinterpret_cast<const V *>(csrc + (size_t)c * dsub);
+                } else {
+                    v[u] = __ldg(reinterpret_cast<const V *>(csrc + (size_t)c * dsub));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                const long long rr = row + (long long)u * rows_par;
+                if (rr < r1) {
+                    float *dst = out + rr * ldo + out_col;
                     if (out_vec_ok) {
                         store_streaming<PW>(dst, v[u]);
                     } else {  // misaligned output view: scalar stores
@@ -140,9 +147,9 @@ rb_status launch_pw(const DeviceCodebook &cb, const void *codes, int code_width,
     const int out_vec_ok =
         ((reinterpret_cast<uintptr_t>(out) % (PW * sizeof(float))) == 0 && (ldo % PW) == 0) ? 1 : 0;
 
-    // column groups: as many subquantizers as fit in ~96 KB of shared memory (2 blocks / SM)
+    // column groups: as many subquantizers as fit in ~100 KB of shared memory (2 blocks of 512 threads / SM)
     const size_t per_m = (size_t)k * dsub * sizeof(float);
-    const size_t budget = 96 * 1024;
+    const size_t budget = 100 * 1024;
     int m_per_group = (int)(budget / per_m);
     const bool smem_cb = m_per_group >= 1;
     if (!smem_cb) m_per_group = M;
@@ -152,7 +159,7 @@ rb_status launch_pw(const DeviceCodebook &cb, const void *codes, int code_width,
     m_per_group = (int)ceil_div(M, n_groups);
     const size_t smem = smem_cb ? (size_t)m_per_group * per_m : 0;
 
-    // row strips: about 2 waves of 2 blocks/SM over all groups, at least 64 rows each
+    // row strips: 2 waves of 2 blocks/SM over all groups, at least 64 rows each
     size_t strips = ceil_div((size_t)148 * 4, (size_t)n_groups);
     size_t rows_per_block = ceil_div(n, strips);
     if (rows_per_block < 64) rows_per_block = 64;
@@ -160,14 +167,15 @@ rb_status launch_pw(const DeviceCodebook &cb, const void *codes, int code_width,
     dim3 grid((unsigned)strips, (unsigned)n_groups);
 
     if (smem_cb) {
-        auto kern = gather_kernel<PW, true>;
+        auto kern = code_width == 1 ? gather_kernel<PW, true, 1> : gather_kernel<PW, true, 0>;
         if (smem > 48 * 1024)
             RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kGatherThreads, smem, stream>>>(cb.quantizers, k, dsub, M, codes, code_width, (long long)n,
                                                     (long long)crs, (long long)ccs, out, (long long)ldo,
                                                     m_per_group, (long long)rows_per_block, err_flag, out_vec_ok);
     } else {
-        gather_kernel<PW, false><<<grid, kGatherThreads, 0, stream>>>(
+        auto kern = code_width == 1 ? gather_kernel<PW, false, 1> : gather_kernel<PW, false, 0>;
+        kern<<<grid, kGatherThreads, 0, stream>>>(
             cb.quantizers, k, dsub, M, codes, code_width, (long long)n, (long long)crs, (long long)ccs, out,
             (long long)ldo, m_per_group, (long long)rows_per_block, err_flag, out_vec_ok);
     }
