@@ -103,7 +103,7 @@ static rb_status encode_device(const DeviceCodebook &cb, const TensorOperands *t
                                cudaStream_t stream)
 {
     int algo = g_encode_algo.load();
-    const bool tc_ok = tc != nullptr && tc->ready() && !seq_norm && tensor_path_supported(cb);
+    const bool tc_ok = tc != nullptr && tc->ready() && !seq_norm && tensor_call_supported(cb, x, n, ldx);
     if (algo == RB_ENCODE_TENSOR && !tc_ok)
         return fail(RB_ERR_UNSUPPORTED, "tensor encode path does not cover this shape (k=%zu, dsub=%zu)", cb.k, cb.dsub);
     if (algo == RB_ENCODE_AUTO) algo = tc_ok ? RB_ENCODE_TENSOR : RB_ENCODE_EXACT;

@@ -158,6 +158,11 @@ struct DeviceCodebook {
 rb_status launch_encode_exact(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx,
                               void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs, int seq_norm,
                               cudaStream_t stream);
+// Same kernel, but it returns immediately unless *gate > gate_thr (gate == nullptr: always runs).  Used by the
+// tensor path as its on-device fallback when the list of undecided pairs overflowed.
+rb_status launch_encode_exact_gated(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx, void *codes,
+                                    int code_width, ptrdiff_t crs, ptrdiff_t ccs, int seq_norm, const uint32_t *gate,
+                                    uint32_t gate_thr, cudaStream_t stream);
 // ||c||^2 for every centroid.
 rb_status launch_centroid_norms(const float *quantizers, size_t rows, size_t dsub, float *cs,
                                 cudaStream_t stream);

@@ -75,9 +75,11 @@ template <int DSUB, int RPT>
 __global__ void __launch_bounds__(kThreads)
 encode_exact_kernel(const float *__restrict__ quantizers, const float *__restrict__ cs_all, int M, int k,
                     int kch, const float *__restrict__ x, long long n, long long ldx, void *codes,
-                    int code_width, long long crs, long long ccs, int seq_norm, int m_per_block)
+                    int code_width, long long crs, long long ccs, int seq_norm, int m_per_block,
+                    const uint32_t *__restrict__ gate, uint32_t gate_thr)
 {
     extern __shared__ __align__(16) float smem[];
+    if (gate != nullptr && *gate <= gate_thr) return;  // gated fallback of the tensor path: nothing overflowed
     float *cen = smem;                      // [kch][DSUB]
     float *csm = smem + (size_t)kch * DSUB; // [kch]
 
@@ -153,8 +155,10 @@ encode_exact_kernel(const float *__restrict__ quantizers, const float *__restric
 __global__ void __launch_bounds__(kThreads)
 encode_exact_generic_kernel(const float *__restrict__ quantizers, const float *__restrict__ cs_all, int M, int k,
                             int dsub, const float *__restrict__ x, long long n, long long ldx, void *codes,
-                            int code_width, long long crs, long long ccs, int seq_norm, int m_per_block)
+                            int code_width, long long crs, long long ccs, int seq_norm, int m_per_block,
+                            const uint32_t *__restrict__ gate, uint32_t gate_thr)
 {
+    if (gate != nullptr && *gate <= gate_thr) return;
     const long long row = (long long)blockIdx.x * kThreads + threadIdx.x;
     if (row >= n) return;
     const int m0 = blockIdx.y * m_per_block;
@@ -256,7 +260,7 @@ encode_recheck_kernel(const float *__restrict__ quantizers, const float *__restr
 
 template <int DSUB>
 rb_status launch_t(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx, void *codes, int code_width,
-                   ptrdiff_t crs, ptrdiff_t ccs, int seq_norm, cudaStream_t stream)
+                   ptrdiff_t crs, ptrdiff_t ccs, int seq_norm, const uint32_t *gate, uint32_t gate_thr, cudaStream_t stream)
 {
     constexpr int RPT = DSUB <= 16 ? 4 : 2;
     const int k = (int)cb.k, M = (int)cb.M;
@@ -271,7 +275,7 @@ rb_status launch_t(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t
     dim3 grid((unsigned)row_tiles, (unsigned)ceil_div(M, m_per_block));
     encode_exact_kernel<DSUB, RPT><<<grid, kThreads, smem, stream>>>(
         cb.quantizers, cb.cs, M, k, kch, x, (long long)n, (long long)ldx, codes, code_width, (long long)crs,
-        (long long)ccs, seq_norm, m_per_block);
+        (long long)ccs, seq_norm, m_per_block, gate, gate_thr);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
@@ -281,13 +285,20 @@ rb_status launch_t(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t
 rb_status launch_encode_exact(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx, void *codes,
                               int code_width, ptrdiff_t crs, ptrdiff_t ccs, int seq_norm, cudaStream_t stream)
 {
+    return launch_encode_exact_gated(cb, x, n, ldx, codes, code_width, crs, ccs, seq_norm, nullptr, 0, stream);
+}
+
+rb_status launch_encode_exact_gated(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx, void *codes,
+                                    int code_width, ptrdiff_t crs, ptrdiff_t ccs, int seq_norm, const uint32_t *gate,
+                                    uint32_t gate_thr, cudaStream_t stream)
+{
     if (n == 0) return RB_OK;
     if (cb.k > (size_t)INT32_MAX || cb.M > (size_t)INT32_MAX || cb.dsub > (size_t)INT32_MAX) {
         set_error("codebook extents exceed 2^31");
         return RB_ERR_UNSUPPORTED;
     }
 #define RB_CASE(D) \
-    case D: return launch_t<D>(cb, x, n, ldx, codes, code_width, crs, ccs, seq_norm, stream);
+    case D: return launch_t<D>(cb, x, n, ldx, codes, code_width, crs, ccs, seq_norm, gate, gate_thr, stream);
     switch (cb.dsub) {
         RB_CASE(1) RB_CASE(2) RB_CASE(3) RB_CASE(4) RB_CASE(5) RB_CASE(6) RB_CASE(7) RB_CASE(8)
         RB_CASE(9) RB_CASE(10) RB_CASE(12) RB_CASE(15) RB_CASE(16) RB_CASE(20) RB_CASE(24) RB_CASE(25)
@@ -302,7 +313,8 @@ rb_status launch_encode_exact(const DeviceCodebook &cb, const float *x, size_t n
     dim3 grid((unsigned)row_tiles, (unsigned)ceil_div(M, m_per_block));
     encode_exact_generic_kernel<<<grid, kThreads, 0, stream>>>(cb.quantizers, cb.cs, M, (int)cb.k, (int)cb.dsub, x,
                                                              (long long)n, (long long)ldx, codes, code_width,
-                                                             (long long)crs, (long long)ccs, seq_norm, m_per_block);
+                                                             (long long)crs, (long long)ccs, seq_norm, m_per_block, gate,
+                                                             gate_thr);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }

@@ -1,19 +1,658 @@
-// encode_tc.cu — tcgen05 tensor-core encode path (placeholder until the kernel lands: reports "not ready",
-// so RB_ENCODE_AUTO resolves to the exact SIMT kernel and RB_ENCODE_TENSOR fails loudly).
+// encode_tc.cu — nearest-centroid encode on the 5th-generation tensor cores (tcgen05, sm_100a), bit-exact.
+//
+// Replaces the same reference chain as encode_exact.cu
+//   primitives::quantize_batch_into (src/pq/primitives.rs:64-104) -> kmeans::cluster_assignments
+//   (src/kmeans.rs:133-159) -> SquaredEuclideanDistance<Ix2> (src/linalg.rs:150-180)
+// for k = 256 centroids.  The reference's decision for one (row, subquantizer) is
+//   argmin_j  d_j,   d_j = fl(fl(xs + cs_j) - fl(2 dp_j)),  dp_j a sequential FP32 FMA chain      (linalg.rs:167-176)
+// which cannot be reproduced bit for bit by a tensor-core contraction.  What can be done exactly is to DECIDE the
+// argmin from a high-precision approximation whenever the decision is not close:
+//
+//   1. Scores  s~_j = cs_j - 2 x.c_j  for all 256 centroids come from tcgen05.mma (M=128 rows, N=256, FP32
+//      accumulators in tensor memory).  Operands are two-limb FP16 splits (x = xh + xl, c = ch + cl, 22 significant
+//      bits each) of the power-of-two-scaled inputs; the three products xh.ch + xh.cl + xl.ch and the two-limb
+//      ||c||^2 are laid along K (K = 3*dsub + 2, padded to a multiple of 16), so one accumulator holds the finished
+//      score to ~2^-21 relative accuracy.  xs is the same for every j and is left out.
+//   2. Each epilogue thread owns one row (one TMEM lane) and scans its 256 scores with 3-input minima along two
+//      partitions of the index set — 16 blocks of 16 consecutive centroids and 16 interleaved chains (j mod 16).
+//      The minimum appears once in each partition; every other chain / block minimum is the score of some other
+//      centroid, so "exactly one block minimum and exactly one chain minimum lie below min + margin" proves that no
+//      other centroid is within `margin` of the winner, and the two positions give its index (16*block + chain).
+//   3. `margin` is twice a bound on |s~_j - (d_j - xs)| (operand split, tensor accumulation, and the reference's own
+//      FP32 rounding), evaluated per row from ||x||^2 and max_j ||c_j||^2.  Rows that fail the test (true near-ties,
+//      ~1e-4 of them on Gaussian data), rows with non-finite or out-of-range values and rows past a NaN are appended
+//      to a list and re-decided by launch_encode_recheck with the reference's exact expression tree.
+//   The emitted codes are therefore identical to the exact kernel's (and the oracle's) for every input.
+//
+// Data flow of one CTA (persistent, one per SM, 14 warps):
+//   warp 0      producer: per row tile, one cp.async.bulk (TMA engine) per row copies the tile's column slice
+//               (a group of subquantizers) into shared memory; loads the group's B operands when the group changes
+//   warps 2-5   converters: thread = row; split the FP32 subvector into FP16 limbs, write the A operand in the
+//               no-swizzle K-major core-matrix layout, publish the row's margin
+//   warp 1      one thread issues tcgen05.mma (K/16 instructions per unit) and tcgen05.commit
+//   warps 6-13  epilogue, two sets of four warps alternating over the two 256-column accumulators
+// Bounds (C2: 2M x 300, M=30): HBM 4*d + M bytes per vector is the roofline (0.38 ms); the kernel is bound by the
+// CUDA-core scan of the 128 x 256 accumulator (1 min3 per element and partition), see DESIGN.md.
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+
 #include "encode_tc.cuh"
+#include "sm100_ptx.cuh"
 
 namespace rb {
 
-bool tensor_path_supported(const DeviceCodebook &) { return false; }
-rb_status TensorOperands::prepare(const DeviceCodebook &, cudaStream_t) { return RB_OK; }
-void TensorOperands::release() {}
-void TensorOperands::release_async(cudaStream_t) {}
+namespace {
 
-rb_status launch_encode_tensor(const DeviceCodebook &, const TensorOperands &, const float *, size_t, ptrdiff_t,
-                               void *, int, ptrdiff_t, ptrdiff_t, cudaStream_t)
+using namespace ptx;
+
+constexpr int kTile = 128;   // rows per tile (UMMA M)
+constexpr int kCent = 256;   // centroids (UMMA N)
+constexpr int kXStages = 2;
+constexpr int kMargRing = 8;
+constexpr int kThreads = 32 * 14;
+constexpr int kSmemLimit = 227 * 1024;
+
+__host__ __device__ constexpr int kpad_of(int dsub) { return ((3 * dsub + 2 + 15) / 16) * 16; }
+
+// error-bound constants (see header comment, DESIGN.md "tensor encode: margin"); generous by >= 4x
+__device__ __forceinline__ float margin_of(float xs, float csmax, int dsub)
 {
-    set_error("tensor encode path not built");
-    return RB_ERR_UNSUPPORTED;
+    const float e = 1.9073486e-6f * (xs + csmax) + 7.6293945e-6f * sqrtf(xs * csmax) * (1.0f + (float)dsub * 0.03125f);
+    return 2.0f * e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// operand preparation (runs when a codebook is created / after every k-means update)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void tc_absmax_kernel(const float *__restrict__ q, size_t total, const float *__restrict__ cs, size_t M, size_t k,
+                                 float *__restrict__ consts)
+{
+    // consts: [M] csmax | scale | scale2 | bad | absmax   (zeroed before this kernel)
+    unsigned *amax = reinterpret_cast<unsigned *>(consts + M + 3);
+    unsigned local = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned b = __float_as_uint(q[i]) & 0x7fffffffu;  // NaN / Inf compare above every finite value
+        local = max(local, b);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) local = max(local, __shfl_xor_sync(0xffffffffu, local, off));
+    if ((threadIdx.x & 31) == 0 && local) atomicMax(amax, local);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * k; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned b = __float_as_uint(cs[i]) & 0x7fffffffu;
+        atomicMax(reinterpret_cast<unsigned *>(consts + i / k), b);
+    }
+}
+
+__device__ __forceinline__ float scale_from_absmax(float amax, bool &bad)
+{
+    bad = !(amax < 3.0e38f);  // NaN or Inf somewhere in the codebook
+    if (bad || amax == 0.f) return 1.f;
+    int p = ilogbf(amax) + 1;       // amax < 2^p
+    int e = 3 - p;                  // amax * 2^e in [4, 8)
+    e = max(-60, min(60, e));
+    return scalbnf(1.f, e);
+}
+
+template <int DSUB>
+__global__ void tc_prepare_kernel(const float *__restrict__ q, const float *__restrict__ cs, int M, __half *__restrict__ bop,
+                                  float *__restrict__ consts)
+{
+    constexpr int KPAD = kpad_of(DSUB), NCH = KPAD / 8;
+    bool bad;
+    const float scale = scale_from_absmax(consts[M + 3], bad);
+    const float scale2 = scale * scale;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        consts[M + 0] = scale;
+        consts[M + 1] = scale2;
+        consts[M + 2] = bad ? 1.f : 0.f;
+    }
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (m, j)
+    if (idx >= M * kCent) return;
+    const int m = idx / kCent, j = idx % kCent;
+    const float *c = q + (size_t)idx * DSUB;
+    __half kv[KPAD];
+#pragma unroll
+    for (int t = 0; t < KPAD; t++) kv[t] = __float2half_rn(0.f);
+#pragma unroll
+    for (int t = 0; t < DSUB; t++) {
+        const float cv = c[t] * scale;
+        const __half h = __float2half_rn(cv);
+        const __half l = __float2half_rn(cv - __half2float(h));
+        const __half h2 = __float2half_rn(-2.f * __half2float(h));  // exact (|cv| < 8)
+        const __half l2 = __float2half_rn(-2.f * __half2float(l));
+        kv[t] = h2;
+        kv[DSUB + t] = l2;
+        kv[2 * DSUB + t] = h2;
+    }
+    const float csv = cs[idx] * scale2;
+    const __half ch = __float2half_rn(csv);
+    kv[3 * DSUB] = ch;
+    kv[3 * DSUB + 1] = __float2half_rn(csv - __half2float(ch));
+    // [m][chunk][j][8 halves]
+    __half *dst = bop + (size_t)m * NCH * kCent * 8;
+#pragma unroll
+    for (int ch8 = 0; ch8 < NCH; ch8++) {
+        uint4 w;
+        __half2 *hw = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; e++) hw[e] = __halves2half2(kv[ch8 * 8 + 2 * e], kv[ch8 * 8 + 2 * e + 1]);
+        *reinterpret_cast<uint4 *>(dst + ((size_t)ch8 * kCent + j) * 8) = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the encode kernel
+// ---------------------------------------------------------------------------------------------------------
+struct EncParams {
+    const float *x;
+    long long n, ldx;
+    const __half *bop;
+    const float *consts;  // [M] csmax | scale | scale2 | bad | absmax
+    void *codes;
+    int code_width;
+    long long crs, ccs;
+    uint32_t *pairs;
+    uint32_t *n_pairs;
+    uint32_t max_pairs;
+    int M, gm, n_groups, a_stages;
+    long long n_tiles, items_total, items_per_cta;
+};
+
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c)
+{
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float min16(const uint32_t *v)
+{
+    const float t0 = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+    const float t1 = fmin3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+    const float t2 = fmin3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+    const float t3 = fmin3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+    const float t4 = fmin3(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]));
+    const float r0 = fmin3(t0, t1, t2);
+    const float r1 = fmin3(t3, t4, __uint_as_float(v[15]));
+    return fminf(r0, r1);
+}
+
+template <int DSUB>
+__global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams p)
+{
+    constexpr int KPAD = kpad_of(DSUB), NCH = KPAD / 8;
+    constexpr int A_BYTES = NCH * kTile * 16, B_BYTES = NCH * kCent * 16;
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xs_bytes = kTile * p.gm * DSUB * 4;  // one X stage
+    unsigned char *sB = smem;
+    unsigned char *sX = sB + (size_t)p.gm * B_BYTES;
+    unsigned char *sA = sX + (size_t)kXStages * xs_bytes;
+    float *sMarg = reinterpret_cast<float *>(sA + (size_t)p.a_stages * A_BYTES);  // [kMargRing][kTile]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sMarg + kMargRing * kTile);
+    uint64_t *x_full = bars, *x_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 8, *acc_full = bars + 12,
+             *acc_empty = bars + 14, *b_full = bars + 16, *b_free = bars + 17, *drain = bars + 18;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&x_full[i], 1);
+            mbar_init(&x_empty[i], 4);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        for (int i = 0; i < 4; i++) {
+            mbar_init(&a_full[i], 4);
+            mbar_init(&a_empty[i], 1);
+        }
+        mbar_init(b_full, 1);
+        mbar_init(b_free, 1);
+        mbar_init(drain, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long it0 = (long long)blockIdx.x * p.items_per_cta;
+    const long long it1 = min(p.items_total, it0 + p.items_per_cta);
+    const int S = p.a_stages;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        int cur_g = -1;
+        uint32_t n_loads = 0;
+        long long li = 0;
+        for (long long item = it0; item < it1; item++, li++) {
+            const int g = (int)(item / p.n_tiles);
+            const long long t = item % p.n_tiles;
+            const int gm_cur = min(p.gm, p.M - g * p.gm);
+            if (g != cur_g) {
+                if (cur_g >= 0) mbar_wait(b_free, (n_loads - 1) & 1);  // every MMA that read the old operands is done
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(b_full, (uint32_t)gm_cur * B_BYTES);
+                    for (int ml = 0; ml < gm_cur; ml++)
+                        bulk_g2s(sB + (size_t)ml * B_BYTES, p.bop + (size_t)(g * p.gm + ml) * (B_BYTES / 2), B_BYTES, b_full);
+                }
+                cur_g = g;
+                n_loads++;
+            }
+            const int stage = (int)(li & 1);
+            mbar_wait(&x_empty[stage], (uint32_t)(((li >> 1) & 1) ^ 1));
+            const long long row0 = t * kTile;
+            const int rows_valid = (int)min((long long)kTile, p.n - row0);
+            const uint32_t slice_bytes = (uint32_t)gm_cur * DSUB * 4;
+            if (lane == 0) mbar_arrive_expect_tx(&x_full[stage], (uint32_t)rows_valid * slice_bytes);
+            __syncwarp();
+            unsigned char *dst = sX + (size_t)stage * xs_bytes;
+            const float *src = p.x + (long long)g * p.gm * DSUB;
+            for (int r = lane; r < rows_valid; r += 32)
+                bulk_g2s(dst + (size_t)r * slice_bytes, src + (row0 + r) * p.ldx, slice_bytes, &x_full[stage]);
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_f16(kTile, kCent, 0);
+            int cur_g = -1;
+            uint32_t n_loads = 0, u = 0;
+            for (long long item = it0; item < it1; item++) {
+                const int g = (int)(item / p.n_tiles);
+                const int gm_cur = min(p.gm, p.M - g * p.gm);
+                if (g != cur_g) {
+                    if (cur_g >= 0) {
+                        tc_commit(drain);
+                        mbar_wait(drain, (n_loads - 1) & 1);
+                        mbar_arrive(b_free);
+                    }
+                    mbar_wait(b_full, n_loads & 1);
+                    n_loads++;
+                    cur_g = g;
+                }
+                for (int ml = 0; ml < gm_cur; ml++, u++) {
+                    const uint32_t as = u % S, buf = u & 1;
+                    mbar_wait(&a_full[as], (u / S) & 1);
+                    mbar_wait(&acc_empty[buf], ((u >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + (size_t)as * A_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + (size_t)ml * B_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < KPAD / 16; ks++) {
+                        const uint64_t ad = smem_desc_kmajor(a_addr + ks * 2 * kTile * 16, kTile * 16, 128);
+                        const uint64_t bd = smem_desc_kmajor(b_addr + ks * 2 * kCent * 16, kCent * 16, 128);
+                        mma_f16_ss(tmem_base + buf * kCent, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                    }
+                    tc_commit(&a_empty[as]);
+                    tc_commit(&acc_full[buf]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ===================== converters (thread = row) =====================
+        const int row = (warp - 2) * 32 + lane;
+        const float scale = p.consts[p.M + 0];
+        const float scale2 = p.consts[p.M + 1];
+        const bool cb_bad = p.consts[p.M + 2] != 0.f;
+        uint32_t u = 0;
+        long long li = 0;
+        for (long long item = it0; item < it1; item++, li++) {
+            const int g = (int)(item / p.n_tiles);
+            const long long t = item % p.n_tiles;
+            const int gm_cur = min(p.gm, p.M - g * p.gm);
+            const int stage = (int)(li & 1);
+            const bool valid = t * kTile + row < p.n;
+            mbar_wait(&x_full[stage], (uint32_t)((li >> 1) & 1));
+            const float *xr = reinterpret_cast<const float *>(sX + (size_t)stage * xs_bytes) + (size_t)row * gm_cur * DSUB;
+            for (int ml = 0; ml < gm_cur; ml++, u++) {
+                float xv[DSUB];
+                if (valid) {
+                    const float *src = xr + ml * DSUB;
+                    if constexpr (DSUB % 4 == 0) {
+#pragma unroll
+                        for (int t4 = 0; t4 < DSUB; t4 += 4) {
+                            const float4 v = *reinterpret_cast<const float4 *>(src + t4);
+                            xv[t4] = v.x; xv[t4 + 1] = v.y; xv[t4 + 2] = v.z; xv[t4 + 3] = v.w;
+                        }
+                    } else if constexpr (DSUB % 2 == 0) {
+#pragma unroll
+                        for (int t2 = 0; t2 < DSUB; t2 += 2) {
+                            const float2 v = *reinterpret_cast<const float2 *>(src + t2);
+                            xv[t2] = v.x; xv[t2 + 1] = v.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int t1 = 0; t1 < DSUB; t1++) xv[t1] = src[t1];
+                    }
+                } else {
+#pragma unroll
+                    for (int t1 = 0; t1 < DSUB; t1++) xv[t1] = 0.f;
+                }
+                __half kv[KPAD];
+#pragma unroll
+                for (int t1 = 0; t1 < KPAD; t1++) kv[t1] = __float2half_rn(0.f);
+                float xs = 0.f;
+                bool bad = cb_bad;
+#pragma unroll
+                for (int t1 = 0; t1 < DSUB; t1++) {
+                    const float sv = xv[t1] * scale;
+                    xs = fmaf(xv[t1], xv[t1], xs);
+                    bad |= !(fabsf(sv) <= 32768.f);  // NaN, Inf or beyond the FP16 range
+                    const __half h = __float2half_rn(sv);
+                    const __half l = __float2half_rn(sv - __half2float(h));
+                    kv[t1] = h;
+                    kv[DSUB + t1] = h;
+                    kv[2 * DSUB + t1] = l;
+                }
+                kv[3 * DSUB] = __float2half_rn(1.f);
+                kv[3 * DSUB + 1] = __float2half_rn(1.f);
+                const float csmax = p.consts[g * p.gm + ml];
+                float marg = margin_of(xs, csmax, DSUB) * scale2;
+                if (bad || !(marg < 3.0e38f)) marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
+
+                const uint32_t as = u % S;
+                mbar_wait(&a_empty[as], ((u / S) & 1) ^ 1);
+                unsigned char *a = sA + (size_t)as * A_BYTES;
+#pragma unroll
+                for (int c8 = 0; c8 < NCH; c8++) {
+                    uint4 w;
+                    __half2 *hw = reinterpret_cast<__half2 *>(&w);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) hw[e] = __halves2half2(kv[c8 * 8 + 2 * e], kv[c8 * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4 *>(a + ((size_t)c8 * kTile + row) * 16) = w;
+                }
+                sMarg[(u % kMargRing) * kTile + row] = marg;
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[as]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_empty[stage]);
+        }
+    } else {
+        // ===================== epilogue (thread = row = TMEM lane) =====================
+        const int set = (warp - 6) >> 2;
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * kCent;
+        const float INF = __int_as_float(0x7f800000);
+        uint32_t u = 0;
+        for (long long item = it0; item < it1; item++) {
+            const int g = (int)(item / p.n_tiles);
+            const long long t = item % p.n_tiles;
+            const int gm_cur = min(p.gm, p.M - g * p.gm);
+            const long long grow = t * kTile + row;
+            for (int ml = 0; ml < gm_cur; ml++, u++) {
+                if ((int)(u & 1) != set) continue;
+                mbar_wait(&acc_full[set], (u >> 1) & 1);
+                tc_fence_after();
+                const float marg = sMarg[(u % kMargRing) * kTile + row];
+                float A[16], B[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) A[i] = INF;
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+#pragma unroll
+                for (int c0 = 0; c0 < kCent; c0 += 64) {
+                    tmem_wait_ld(v0);
+                    tmem_ld32(taddr + c0 + 32, v1);
+                    B[c0 / 16] = min16(v0);
+                    B[c0 / 16 + 1] = min16(v0 + 16);
+#pragma unroll
+                    for (int a = 0; a < 16; a++) A[a] = fmin3(A[a], __uint_as_float(v0[a]), __uint_as_float(v0[16 + a]));
+                    tmem_wait_ld(v1);
+                    if (c0 + 64 < kCent) tmem_ld32(taddr + c0 + 64, v0);
+                    B[c0 / 16 + 2] = min16(v1);
+                    B[c0 / 16 + 3] = min16(v1 + 16);
+#pragma unroll
+                    for (int a = 0; a < 16; a++) A[a] = fmin3(A[a], __uint_as_float(v1[a]), __uint_as_float(v1[16 + a]));
+                }
+                // the accumulator is free again
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[set]);
+
+                float m1 = fmin3(B[0], B[1], B[2]);
+                m1 = fmin3(m1, B[3], B[4]);
+                m1 = fmin3(m1, B[5], B[6]);
+                m1 = fmin3(m1, B[7], B[8]);
+                m1 = fmin3(m1, B[9], B[10]);
+                m1 = fmin3(m1, B[11], B[12]);
+                m1 = fmin3(m1, B[13], B[14]);
+                m1 = fminf(m1, B[15]);
+                // count the block / chain minima below m1 + margin and pick up their positions (FMA pipe):
+                // t = sat((thr - v) * 2^40) is 1 for v < thr (by at least one ulp), 0 for v >= thr and for NaN
+                const float thr = m1 + marg;
+                const float SC = 1.099511627776e12f;  // 2^40
+                const float thr_sc = thr * SC;
+                float cb = 0.f, ib = 0.f, ca = 0.f, ia = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float tb = fma_sat(B[i], -SC, thr_sc);
+                    cb += tb;
+                    ib = fmaf(tb, (float)i, ib);
+                    const float ta = fma_sat(A[i], -SC, thr_sc);
+                    ca += ta;
+                    ia = fmaf(ta, (float)i, ia);
+                }
+                const bool certain = (cb == 1.f) && (ca == 1.f) && (marg == marg) && (fabsf(m1) < 3.0e38f);
+                if (grow < p.n) {
+                    const int m = g * p.gm + ml;
+                    unsigned code = certain ? (unsigned)((int)ib * 16 + (int)ia) : 0u;
+                    store_code(p.codes, p.code_width, grow * p.crs + (long long)m * p.ccs, code);
+                    if (!certain) {
+                        const uint32_t slot = atomicAdd(p.n_pairs, 1u);
+                        if (slot < p.max_pairs) {
+                            p.pairs[2 * (size_t)slot] = (uint32_t)grow;
+                            p.pairs[2 * (size_t)slot + 1] = (uint32_t)m;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+struct Plan {
+    int gm = 0, n_groups = 0, a_stages = 0;
+    size_t smem = 0;
+};
+
+Plan make_plan(size_t M, size_t dsub)
+{
+    Plan best;
+    const size_t kpad = (size_t)kpad_of((int)dsub), nch = kpad / 8;
+    const size_t a_bytes = nch * kTile * 16, b_bytes = nch * kCent * 16;
+    if ((M * dsub) % 4 != 0) return best;
+    for (size_t gm = M < 8 ? M : 8; gm >= 1; gm--) {
+        if ((gm * dsub) % 4 != 0) continue;
+        for (int stages = 3; stages >= 2; stages--) {
+            const size_t smem = gm * b_bytes + (size_t)kXStages * kTile * gm * dsub * 4 + (size_t)stages * a_bytes +
+                                (size_t)kMargRing * kTile * 4 + 24 * 8;
+            if (smem <= (size_t)kSmemLimit - 1024) {
+                best.gm = (int)gm;
+                best.n_groups = (int)ceil_div(M, gm);
+                best.a_stages = stages;
+                best.smem = smem;
+                return best;
+            }
+        }
+    }
+    return best;
+}
+
+template <int DSUB>
+rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const float *x, size_t n, ptrdiff_t ldx, void *codes,
+                   int code_width, ptrdiff_t crs, ptrdiff_t ccs, uint32_t *pairs, uint32_t *n_pairs, uint32_t max_pairs,
+                   cudaStream_t stream)
+{
+    const Plan plan = make_plan(cb.M, cb.dsub);
+    EncParams p;
+    p.x = x;
+    p.n = (long long)n;
+    p.ldx = (long long)ldx;
+    p.bop = reinterpret_cast<const __half *>(tc.b_tiles);
+    p.consts = tc.consts;
+    p.codes = codes;
+    p.code_width = code_width;
+    p.crs = (long long)crs;
+    p.ccs = (long long)ccs;
+    p.pairs = pairs;
+    p.n_pairs = n_pairs;
+    p.max_pairs = max_pairs;
+    p.M = (int)cb.M;
+    p.gm = plan.gm;
+    p.n_groups = plan.n_groups;
+    p.a_stages = plan.a_stages;
+    p.n_tiles = (long long)ceil_div(n, (size_t)kTile);
+    p.items_total = p.n_tiles * plan.n_groups;
+    int dev = 0, sms = 148;
+    RB_CUDA_TRY(cudaGetDevice(&dev));
+    RB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long ctas = p.items_total < sms ? p.items_total : sms;
+    p.items_per_cta = (p.items_total + ctas - 1) / ctas;
+    ctas = (p.items_total + p.items_per_cta - 1) / p.items_per_cta;
+    auto kern = encode_tc_kernel<DSUB>;
+    RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    kern<<<(unsigned)ctas, kThreads, plan.smem, stream>>>(p);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+#define RB_TC_DSUBS(X) X(4) X(8) X(10) X(12) X(16) X(20) X(30)
+
+bool dsub_instantiated(size_t dsub)
+{
+    switch (dsub) {
+#define X(D) case D:
+        RB_TC_DSUBS(X)
+#undef X
+        return true;
+    default: return false;
+    }
+}
+
+}  // namespace
+
+bool tensor_path_supported(const DeviceCodebook &cb)
+{
+    if (cb.k != (size_t)kCent || !dsub_instantiated(cb.dsub)) return false;
+    return make_plan(cb.M, cb.dsub).gm > 0;
+}
+
+bool tensor_call_supported(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx)
+{
+    if (!tensor_path_supported(cb)) return false;
+    if (n == 0 || n >= ((size_t)1 << 32)) return false;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return false;
+    if (ldx < (ptrdiff_t)(cb.M * cb.dsub) || (ldx % 4) != 0) return false;
+    return true;
+}
+
+rb_status TensorOperands::prepare(const DeviceCodebook &cb, cudaStream_t stream)
+{
+    if (!tensor_path_supported(cb)) return RB_OK;  // stays !ready(): callers use the exact kernel
+    kpad = kpad_of((int)cb.dsub);
+    const size_t b_bytes = cb.M * (size_t)(kpad / 8) * kCent * 16;
+    const size_t c_bytes = (cb.M + 4) * sizeof(float);
+    if (!b_tiles) {
+        RB_CUDA_TRY(cudaMallocAsync(&b_tiles, b_bytes + c_bytes, stream));
+        bytes = b_bytes + c_bytes;
+    }
+    consts = reinterpret_cast<float *>(reinterpret_cast<char *>(b_tiles) + b_bytes);
+    RB_CUDA_TRY(cudaMemsetAsync(consts, 0, c_bytes, stream));
+    tc_absmax_kernel<<<148, 256, 0, stream>>>(cb.quantizers, cb.M * cb.k * cb.dsub, cb.cs, cb.M, cb.k, consts);
+    RB_LAUNCH_CHECK();
+    const unsigned blocks = (unsigned)ceil_div(cb.M * (size_t)kCent, 128);
+    switch (cb.dsub) {
+#define X(D)                                                                                                         \
+    case D:                                                                                                          \
+        tc_prepare_kernel<D><<<blocks, 128, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.M,                            \
+                                                         reinterpret_cast<__half *>(b_tiles), consts);               \
+        break;
+        RB_TC_DSUBS(X)
+#undef X
+    default: break;
+    }
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+void TensorOperands::release()
+{
+    if (b_tiles) cudaFree(b_tiles);
+    b_tiles = nullptr;
+    consts = nullptr;
+}
+
+void TensorOperands::release_async(cudaStream_t stream)
+{
+    if (b_tiles) cudaFreeAsync(b_tiles, stream);
+    b_tiles = nullptr;
+    consts = nullptr;
+}
+
+rb_status launch_encode_tensor(const DeviceCodebook &cb, const TensorOperands &tc, const float *x, size_t n, ptrdiff_t ldx,
+                               void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream)
+{
+    if (n == 0) return RB_OK;
+    if (!tc.ready() || !tensor_call_supported(cb, x, n, ldx)) {
+        set_error("tensor encode path does not cover this call (k=%zu, dsub=%zu, ldx=%td)", cb.k, cb.dsub, ldx);
+        return RB_ERR_UNSUPPORTED;
+    }
+    // list of (row, subquantizer) pairs the tensor pass could not decide; when it overflows the whole batch is
+    // re-encoded by the exact kernel (gated on the device, no host round trip)
+    const size_t units = n * cb.M;
+    size_t cap = units / 8 + 4096;
+    if (cap > 0x7fffffffull) cap = 0x7fffffffull;
+    uint32_t *work = nullptr;
+    RB_CUDA_TRY(cudaMallocAsync(&work, (2 * cap + 4) * sizeof(uint32_t), stream));
+    uint32_t *n_pairs = work, *pairs = work + 4;
+    rb_status st = RB_OK;
+    auto body = [&]() -> rb_status {
+        RB_CUDA_TRY(cudaMemsetAsync(n_pairs, 0, 4 * sizeof(uint32_t), stream));
+        switch (cb.dsub) {
+#define X(D)                                                                                                         \
+    case D:                                                                                                          \
+        RB_TRY(launch_t<D>(cb, tc, x, n, ldx, codes, code_width, crs, ccs, pairs, n_pairs, (uint32_t)cap, stream));  \
+        break;
+            RB_TC_DSUBS(X)
+#undef X
+        default: break;
+        }
+        if (getenv("RB_TC_STATS")) {  // debugging aid: how many (row, subquantizer) pairs the tensor pass left undecided
+            uint32_t np_host = 0;
+            RB_CUDA_TRY(cudaMemcpyAsync(&np_host, n_pairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            RB_CUDA_TRY(cudaStreamSynchronize(stream));
+            fprintf(stderr, "[rb tc] n=%zu M=%zu dsub=%zu: %u of %zu pairs re-decided exactly (%.4f%%)\n", n, cb.M, cb.dsub,
+                    np_host, units, 100.0 * np_host / (double)units);
+        }
+        RB_TRY(launch_encode_recheck(cb, x, ldx, pairs, n_pairs, (uint32_t)cap, codes, code_width, crs, ccs, stream));
+        RB_TRY(launch_encode_exact_gated(cb, x, n, ldx, codes, code_width, crs, ccs, 0, n_pairs, (uint32_t)cap, stream));
+        return RB_OK;
+    };
+    st = body();
+    cudaFreeAsync(work, stream);
+    return st;
 }
 
 }  // namespace rb

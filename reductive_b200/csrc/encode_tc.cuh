@@ -4,19 +4,22 @@
 
 namespace rb {
 
-// Codebook operands in the layout the tensor kernel consumes (built once per codebook).
+// Codebook operands in the layout the tensor kernel consumes (rebuilt whenever the centroids change).
 struct TensorOperands {
-    void *b_tiles = nullptr;   // bf16 split codebook, UMMA K-major core-matrix layout, per subquantizer
-    float *row_bound = nullptr;  // [M] per-subquantizer max ||c||, for the error bound
+    void *b_tiles = nullptr;     // fp16 two-limb codebook, UMMA K-major core-matrix layout: [M][kpad/8][256][8 halves]
+    float *consts = nullptr;     // [M] max_j ||c_j||^2 per subquantizer, then 4 floats: scale 2^e, 2^2e, bad flag, |c|max
     size_t bytes = 0;
-    int kpad = 0;       // K extent (multiple of 16) of the augmented operand
+    int kpad = 0;                // K extent (multiple of 16) of the augmented operand: 3*dsub + 2 rounded up
     bool ready() const { return b_tiles != nullptr; }
     rb_status prepare(const DeviceCodebook &cb, cudaStream_t stream);
     void release();
     void release_async(cudaStream_t stream);
 };
 
+// Shapes the tensor kernel covers (k == 256 centroids, subvector widths it is instantiated for).
 bool tensor_path_supported(const DeviceCodebook &cb);
+// ... and the per-call conditions (alignment of x / ldx, n < 2^32).
+bool tensor_call_supported(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx);
 
 rb_status launch_encode_tensor(const DeviceCodebook &cb, const TensorOperands &tc, const float *x, size_t n,
                                ptrdiff_t ldx, void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs,
