@@ -33,6 +33,7 @@
 //   warps 6-13  epilogue, two sets of four warps alternating over the two 256-column accumulators
 // Bounds (C2: 2M x 300, M=30): HBM 4*d + M bytes per vector is the roofline (0.38 ms); the kernel is bound by the
 // CUDA-core scan of the 128 x 256 accumulator (1 min3 per element and partition), see DESIGN.md.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <cstdio>
@@ -52,6 +53,9 @@ constexpr int kCent = 256;   // centroids (UMMA N)
 constexpr int kXStages = 2;
 constexpr int kMargRing = 8;
 constexpr int kThreads = 32 * 14;
+// Warp roles.  The SM's warp arbiter favours higher warp ids, so the roles every other warp waits on (producer, MMA
+// issuer, converters) sit above the eight epilogue warps (whose TMEM lane quarter is warp % 4).
+constexpr int kWarpConv0 = 8, kWarpMma = 12, kWarpProducer = 13;
 constexpr int kSmemLimit = 227 * 1024;
 
 __host__ __device__ constexpr int kpad_of(int dsub) { return ((3 * dsub + 2 + 15) / 16) * 16; }
@@ -59,7 +63,8 @@ __host__ __device__ constexpr int kpad_of(int dsub) { return ((3 * dsub + 2 + 15
 // error-bound constants (see header comment, DESIGN.md "tensor encode: margin"); generous by >= 4x
 __device__ __forceinline__ float margin_of(float xs, float csmax, int dsub)
 {
-    const float e = 1.9073486e-6f * (xs + csmax) + 7.6293945e-6f * sqrtf(xs * csmax) * (1.0f + (float)dsub * 0.03125f);
+    // sqrt(xs * csmax) <= (xs + csmax) / 2
+    const float e = (1.9073486e-6f + 3.8146973e-6f * (1.0f + (float)dsub * 0.03125f)) * (xs + csmax);
     return 2.0f * e;
 }
 
@@ -185,7 +190,7 @@ __device__ __forceinline__ float min16(const uint32_t *v)
 }
 
 template <int DSUB>
-__global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams p)
+__global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int KPAD = kpad_of(DSUB), NCH = KPAD / 8;
     constexpr int A_BYTES = NCH * kTile * 16, B_BYTES = NCH * kCent * 16;
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
         mbar_init(drain, 1);
         fence_mbar_init();
     }
-    if (warp == 1) {
+    if (warp == kWarpMma) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -231,43 +236,39 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
     const long long it1 = min(p.items_total, it0 + p.items_per_cta);
     const int S = p.a_stages;
 
-    if (warp == 0) {
+    if (warp == kWarpProducer) {
         // ===================== producer =====================
-        int cur_g = -1;
-        uint32_t n_loads = 0;
-        long long li = 0;
-        for (long long item = it0; item < it1; item++, li++) {
-            const int g = (int)(item / p.n_tiles);
-            const long long t = item % p.n_tiles;
-            const int gm_cur = min(p.gm, p.M - g * p.gm);
-            if (g != cur_g) {
-                if (cur_g >= 0) mbar_wait(b_free, (n_loads - 1) & 1);  // every MMA that read the old operands is done
-                if (lane == 0) {
+        if (lane == 0) {
+            prefetch_tensormap(&tmap);
+            int cur_g = -1;
+            uint32_t n_loads = 0;
+            long long li = 0;
+            for (long long item = it0; item < it1; item++, li++) {
+                const int g = (int)(item / p.n_tiles);
+                const long long t = item % p.n_tiles;
+                const int gm_cur = min(p.gm, p.M - g * p.gm);
+                if (g != cur_g) {
+                    if (cur_g >= 0) mbar_wait(b_free, (n_loads - 1) & 1);  // every MMA that read the old operands is done
                     mbar_arrive_expect_tx(b_full, (uint32_t)gm_cur * B_BYTES);
                     for (int ml = 0; ml < gm_cur; ml++)
                         bulk_g2s(sB + (size_t)ml * B_BYTES, p.bop + (size_t)(g * p.gm + ml) * (B_BYTES / 2), B_BYTES, b_full);
+                    cur_g = g;
+                    n_loads++;
                 }
-                cur_g = g;
-                n_loads++;
+                const int stage = (int)(li & 1);
+                mbar_wait(&x_empty[stage], (uint32_t)(((li >> 1) & 1) ^ 1));
+                // one TMA tile load: box = 128 rows x (gm * dsub) floats; rows / columns outside the matrix arrive as zeros
+                mbar_arrive_expect_tx(&x_full[stage], (uint32_t)xs_bytes);
+                tma_load_2d(sX + (size_t)stage * xs_bytes, &tmap, g * p.gm * DSUB, (int)(t * kTile), &x_full[stage]);
             }
-            const int stage = (int)(li & 1);
-            mbar_wait(&x_empty[stage], (uint32_t)(((li >> 1) & 1) ^ 1));
-            const long long row0 = t * kTile;
-            const int rows_valid = (int)min((long long)kTile, p.n - row0);
-            const uint32_t slice_bytes = (uint32_t)gm_cur * DSUB * 4;
-            if (lane == 0) mbar_arrive_expect_tx(&x_full[stage], (uint32_t)rows_valid * slice_bytes);
-            __syncwarp();
-            unsigned char *dst = sX + (size_t)stage * xs_bytes;
-            const float *src = p.x + (long long)g * p.gm * DSUB;
-            for (int r = lane; r < rows_valid; r += 32)
-                bulk_g2s(dst + (size_t)r * slice_bytes, src + (row0 + r) * p.ldx, slice_bytes, &x_full[stage]);
         }
-    } else if (warp == 1) {
+        __syncwarp();
+    } else if (warp == kWarpMma) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = idesc_f16(kTile, kCent, 0);
             int cur_g = -1;
-            uint32_t n_loads = 0, u = 0;
+            uint32_t n_loads = 0, u = 0, as = 0, aph = 0;
             for (long long item = it0; item < it1; item++) {
                 const int g = (int)(item / p.n_tiles);
                 const int gm_cur = min(p.gm, p.M - g * p.gm);
@@ -282,8 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
                     cur_g = g;
                 }
                 for (int ml = 0; ml < gm_cur; ml++, u++) {
-                    const uint32_t as = u % S, buf = u & 1;
-                    mbar_wait(&a_full[as], (u / S) & 1);
+                    const uint32_t buf = u & 1;
+                    mbar_wait(&a_full[as], aph);
                     mbar_wait(&acc_empty[buf], ((u >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + (size_t)as * A_BYTES);
@@ -296,17 +297,21 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
                     }
                     tc_commit(&a_empty[as]);
                     tc_commit(&acc_full[buf]);
+                    if (++as == (uint32_t)S) {
+                        as = 0;
+                        aph ^= 1;
+                    }
                 }
             }
         }
         __syncwarp();
-    } else if (warp < 6) {
+    } else if (warp >= kWarpConv0) {
         // ===================== converters (thread = row) =====================
-        const int row = (warp - 2) * 32 + lane;
+        const int row = (warp - kWarpConv0) * 32 + lane;
         const float scale = p.consts[p.M + 0];
         const float scale2 = p.consts[p.M + 1];
         const bool cb_bad = p.consts[p.M + 2] != 0.f;
-        uint32_t u = 0;
+        uint32_t u = 0, as = 0, aph = 0;
         long long li = 0;
         for (long long item = it0; item < it1; item++, li++) {
             const int g = (int)(item / p.n_tiles);
@@ -315,75 +320,71 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
             const int stage = (int)(li & 1);
             const bool valid = t * kTile + row < p.n;
             mbar_wait(&x_full[stage], (uint32_t)((li >> 1) & 1));
-            const float *xr = reinterpret_cast<const float *>(sX + (size_t)stage * xs_bytes) + (size_t)row * gm_cur * DSUB;
+            const float *xr = reinterpret_cast<const float *>(sX + (size_t)stage * xs_bytes) + (size_t)row * p.gm * DSUB;
             for (int ml = 0; ml < gm_cur; ml++, u++) {
-                float xv[DSUB];
-                if (valid) {
-                    const float *src = xr + ml * DSUB;
-                    if constexpr (DSUB % 4 == 0) {
+                static_assert(DSUB % 2 == 0, "the converter packs pairs of elements");
+                float sv[DSUB];
+                float xs = 0.f, amax = 0.f;
+                {
+                    const float2 *src = reinterpret_cast<const float2 *>(xr + ml * DSUB);
 #pragma unroll
-                        for (int t4 = 0; t4 < DSUB; t4 += 4) {
-                            const float4 v = *reinterpret_cast<const float4 *>(src + t4);
-                            xv[t4] = v.x; xv[t4 + 1] = v.y; xv[t4 + 2] = v.z; xv[t4 + 3] = v.w;
-                        }
-                    } else if constexpr (DSUB % 2 == 0) {
-#pragma unroll
-                        for (int t2 = 0; t2 < DSUB; t2 += 2) {
-                            const float2 v = *reinterpret_cast<const float2 *>(src + t2);
-                            xv[t2] = v.x; xv[t2 + 1] = v.y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int t1 = 0; t1 < DSUB; t1++) xv[t1] = src[t1];
+                    for (int t2 = 0; t2 < DSUB / 2; t2++) {
+                        float2 v = valid ? src[t2] : make_float2(0.f, 0.f);
+                        xs = fmaf(v.x, v.x, xs);
+                        xs = fmaf(v.y, v.y, xs);
+                        sv[2 * t2] = v.x * scale;
+                        sv[2 * t2 + 1] = v.y * scale;
+                        amax = fmaxf(amax, fmaxf(fabsf(sv[2 * t2]), fabsf(sv[2 * t2 + 1])));
                     }
-                } else {
-#pragma unroll
-                    for (int t1 = 0; t1 < DSUB; t1++) xv[t1] = 0.f;
                 }
-                __half kv[KPAD];
+                // two-limb FP16 split, two elements per conversion instruction
+                uint32_t hw[DSUB / 2], lw[DSUB / 2];
 #pragma unroll
-                for (int t1 = 0; t1 < KPAD; t1++) kv[t1] = __float2half_rn(0.f);
-                float xs = 0.f;
-                bool bad = cb_bad;
-#pragma unroll
-                for (int t1 = 0; t1 < DSUB; t1++) {
-                    const float sv = xv[t1] * scale;
-                    xs = fmaf(xv[t1], xv[t1], xs);
-                    bad |= !(fabsf(sv) <= 32768.f);  // NaN, Inf or beyond the FP16 range
-                    const __half h = __float2half_rn(sv);
-                    const __half l = __float2half_rn(sv - __half2float(h));
-                    kv[t1] = h;
-                    kv[DSUB + t1] = h;
-                    kv[2 * DSUB + t1] = l;
+                for (int t2 = 0; t2 < DSUB / 2; t2++) {
+                    const __half2 h = __floats2half2_rn(sv[2 * t2], sv[2 * t2 + 1]);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(sv[2 * t2] - hf.x, sv[2 * t2 + 1] - hf.y);
+                    hw[t2] = *reinterpret_cast<const uint32_t *>(&h);
+                    lw[t2] = *reinterpret_cast<const uint32_t *>(&l);
                 }
-                kv[3 * DSUB] = __float2half_rn(1.f);
-                kv[3 * DSUB + 1] = __float2half_rn(1.f);
+                // K layout [xh | xh | xl | 1 1 | 0 ...] as 32-bit words (two halves each)
+                uint32_t w[KPAD / 2];
+#pragma unroll
+                for (int i = 0; i < KPAD / 2; i++) w[i] = 0u;
+#pragma unroll
+                for (int i = 0; i < DSUB / 2; i++) {
+                    w[i] = hw[i];
+                    w[DSUB / 2 + i] = hw[i];
+                    w[DSUB + i] = lw[i];
+                }
+                w[3 * DSUB / 2] = 0x3c003c00u;  // (1.0, 1.0)
+                // NaN in x makes xs NaN, Inf makes it Inf; |x * scale| beyond the FP16 range: decide such rows exactly
+                const bool bad = cb_bad || !(xs < 3.0e38f) || !(amax <= 32768.f);
                 const float csmax = p.consts[g * p.gm + ml];
                 float marg = margin_of(xs, csmax, DSUB) * scale2;
                 if (bad || !(marg < 3.0e38f)) marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
 
-                const uint32_t as = u % S;
-                mbar_wait(&a_empty[as], ((u / S) & 1) ^ 1);
+                mbar_wait(&a_empty[as], aph ^ 1);
                 unsigned char *a = sA + (size_t)as * A_BYTES;
 #pragma unroll
-                for (int c8 = 0; c8 < NCH; c8++) {
-                    uint4 w;
-                    __half2 *hw = reinterpret_cast<__half2 *>(&w);
-#pragma unroll
-                    for (int e = 0; e < 4; e++) hw[e] = __halves2half2(kv[c8 * 8 + 2 * e], kv[c8 * 8 + 2 * e + 1]);
-                    *reinterpret_cast<uint4 *>(a + ((size_t)c8 * kTile + row) * 16) = w;
-                }
+                for (int c8 = 0; c8 < NCH; c8++)
+                    *reinterpret_cast<uint4 *>(a + ((size_t)c8 * kTile + row) * 16) =
+                        make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
                 sMarg[(u % kMargRing) * kTile + row] = marg;
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[as]);
+                if (++as == (uint32_t)S) {
+                    as = 0;
+                    aph ^= 1;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[stage]);
         }
     } else {
         // ===================== epilogue (thread = row = TMEM lane) =====================
-        const int set = (warp - 6) >> 2;
+        const int set = warp >> 2;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * kCent;
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -500,6 +501,39 @@ Plan make_plan(size_t M, size_t dsub)
     return best;
 }
 
+// 2-D tensor map over the row-major batch: dimension 0 = the d columns, dimension 1 = the n rows (pitch ldx floats);
+// box = one tile's column slice.  cuTensorMapEncodeTiled is resolved through the runtime (no libcuda link).
+rb_status make_x_tensor_map(const float *x, size_t n, size_t d, ptrdiff_t ldx, size_t box_cols, CUtensorMap *out)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = []() -> EncodeFn {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (!encode) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return RB_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kTile};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%zu d=%zu ldx=%td box=%zu)", (int)r, n, d, ldx, box_cols);
+        return RB_ERR_CUDA;
+    }
+    return RB_OK;
+}
+
 template <int DSUB>
 rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const float *x, size_t n, ptrdiff_t ldx, void *codes,
                    int code_width, ptrdiff_t crs, ptrdiff_t ccs, uint32_t *pairs, uint32_t *n_pairs, uint32_t max_pairs,
@@ -531,9 +565,11 @@ rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const flo
     long long ctas = p.items_total < sms ? p.items_total : sms;
     p.items_per_cta = (p.items_total + ctas - 1) / ctas;
     ctas = (p.items_total + p.items_per_cta - 1) / p.items_per_cta;
+    CUtensorMap tmap;
+    RB_TRY(make_x_tensor_map(x, n, cb.M * cb.dsub, ldx, (size_t)plan.gm * cb.dsub, &tmap));
     auto kern = encode_tc_kernel<DSUB>;
     RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    kern<<<(unsigned)ctas, kThreads, plan.smem, stream>>>(p);
+    kern<<<(unsigned)ctas, kThreads, plan.smem, stream>>>(p, tmap);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
