@@ -137,6 +137,205 @@ gather_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, cons
     if (bad) atomicExch(err_flag, 1);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast path (u8 codes, dense [n, M] code matrix, 16-byte aligned output rows, even dsub): tiled gather.
+//
+// A block owns one column group (a whole number of subquantizers whose width in floats is a multiple of 4; its
+// codebook slice lives in shared memory for the block's lifetime) and walks a strip of row tiles.  Per tile the
+// code bytes of the tile's rows are staged in shared memory by coalesced 16-byte loads that were issued one tile
+// AHEAD (register prefetch), so the inner loop has no global-load latency in it: per 16-byte output piece it
+// reads one or two code bytes and one 16-byte / two 8-byte centroid pieces from shared memory and issues one
+// 16-byte global store.  Consecutive lanes own consecutive pieces of a row, so a warp store writes 512 contiguous
+// bytes (row segments of the group).  Blocks of the column groups of one strip have adjacent block indices: they
+// run concurrently and the 32-byte sectors straddling a group boundary are completed in L2.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 512;
+constexpr int kTileVpt = 2;  // 16-byte code vectors prefetched per thread and tile
+
+// piece table entry: where the two 8-byte halves of a 16-byte output piece come from
+struct PieceSrc {
+    uint32_t off0, cc0, off1, cc1;  // float offset into the group's codebook (add code * dsub); code column
+};
+
+template <bool QUAD, bool CHECK>
+__global__ void __launch_bounds__(kTileThreads, 2)
+gather_tile_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, const uint8_t *__restrict__ codes,
+                   long long n, float *__restrict__ out, long long ldo, int m_per_group, int n_groups,
+                   int tile_rows, long long tiles_per_strip, int cb_floats_max, int *__restrict__ err_flag)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int g = blockIdx.x % n_groups;
+    const long long strip = blockIdx.x / n_groups;
+    const int m0 = g * m_per_group;
+    const int mg = min(m_per_group, M - m0);
+    const int w4 = mg * dsub / 4;  // 16-byte pieces per row in this group
+
+    float *cb = reinterpret_cast<float *>(smem_raw);                       // [mg][k][dsub]
+    PieceSrc *tab = reinterpret_cast<PieceSrc *>(cb + cb_floats_max);      // [w4]
+    uint8_t *sc = reinterpret_cast<uint8_t *>(tab + (m_per_group * dsub / 4));  // [tile_rows][M]
+
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(quantizers + (size_t)m0 * k * dsub);
+        float4 *dst = reinterpret_cast<float4 *>(cb);
+        const int total4 = mg * k * dsub / 4;
+        for (int i = threadIdx.x; i < total4; i += kTileThreads) dst[i] = __ldg(src + i);
+        for (int c4 = threadIdx.x; c4 < w4; c4 += kTileThreads) {
+            PieceSrc e;
+            const int col0 = 4 * c4, col1 = 4 * c4 + 2;
+            e.cc0 = col0 / dsub;
+            e.off0 = e.cc0 * k * dsub + col0 % dsub;
+            e.cc1 = col1 / dsub;
+            e.off1 = e.cc1 * k * dsub + col1 % dsub;
+            tab[c4] = e;
+        }
+    }
+
+    const long long tile0 = strip * tiles_per_strip;
+    const long long n_tiles = (n + tile_rows - 1) / tile_rows;
+    const long long tile1 = min(n_tiles, tile0 + tiles_per_strip);
+    const size_t total_code_bytes = (size_t)n * M;
+    const int tile_vecs = tile_rows * M / 16;  // tile_rows * M is a multiple of 16 by construction
+
+    // register prefetch of a tile's code bytes (vectors past the end of the code matrix are skipped; a ragged
+    // last vector is read bytewise)
+    uint4 pre[kTileVpt];
+    auto prefetch = [&](long long tile) {
+        const size_t base = (size_t)tile * tile_rows * M;
+#pragma unroll
+        for (int v = 0; v < kTileVpt; v++) {
+            const int vi = threadIdx.x + v * kTileThreads;
+            const size_t byte0 = base + (size_t)vi * 16;
+            pre[v] = make_uint4(0u, 0u, 0u, 0u);
+            if (vi < tile_vecs && byte0 < total_code_bytes) {
+                if (byte0 + 16 <= total_code_bytes) {
+                    pre[v] = __ldcs(reinterpret_cast<const uint4 *>(codes + byte0));
+                } else {
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int b = 0; b < 16; b++)
+                        if (byte0 + b < total_code_bytes) w[b >> 2] |= (uint32_t)codes[byte0 + b] << (8 * (b & 3));
+                    pre[v] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    };
+
+    const int d_row = kTileThreads / w4, d_c = kTileThreads % w4;
+    const int gcol0 = m0 * dsub;
+    bool bad = false;
+
+    if (tile0 < tile1) prefetch(tile0);
+    for (long long tile = tile0; tile < tile1; tile++) {
+        __syncthreads();  // everyone is done with the previous tile's codes (and, first time, the codebook is in)
+#pragma unroll
+        for (int v = 0; v < kTileVpt; v++) {
+            const int vi = threadIdx.x + v * kTileThreads;
+            if (vi < tile_vecs) reinterpret_cast<uint4 *>(sc)[vi] = pre[v];
+        }
+        __syncthreads();
+        if (tile + 1 < tile1) prefetch(tile + 1);
+
+        const long long r0 = tile * tile_rows;
+        const int rows = (int)min((long long)tile_rows, n - r0);
+        int row = (int)threadIdx.x / w4, c4 = (int)threadIdx.x % w4;
+        float *orow = out + r0 * ldo + gcol0;
+        while (row < rows) {
+            const PieceSrc e = tab[c4];
+            const uint8_t *crow = sc + row * M + m0;
+            float4 v;
+            if constexpr (QUAD) {  // dsub % 4 == 0: the piece lies inside one centroid
+                unsigned c = crow[e.cc0];
+                if constexpr (CHECK) {
+                    bad |= c >= (unsigned)k;
+                    c = min(c, (unsigned)(k - 1));
+                }
+                v = *reinterpret_cast<const float4 *>(cb + e.off0 + c * dsub);
+            } else {
+                unsigned ca = crow[e.cc0], cbb = crow[e.cc1];
+                if constexpr (CHECK) {
+                    bad |= (ca >= (unsigned)k) | (cbb >= (unsigned)k);
+                    ca = min(ca, (unsigned)(k - 1));
+                    cbb = min(cbb, (unsigned)(k - 1));
+                }
+                const float2 lo = *reinterpret_cast<const float2 *>(cb + e.off0 + ca * dsub);
+                const float2 hi = *reinterpret_cast<const float2 *>(cb + e.off1 + cbb * dsub);
+                v = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+            __stcs(reinterpret_cast<float4 *>(orow + (long long)row * ldo + 4 * c4), v);
+            row += d_row;
+            c4 += d_c;
+            if (c4 >= w4) {
+                c4 -= w4;
+                row++;
+            }
+        }
+    }
+    if (bad) atomicExch(err_flag, 1);
+}
+
+// Returns true when the tiled kernel was launched (otherwise the caller uses the generic kernel).
+bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, size_t n, ptrdiff_t crs, ptrdiff_t ccs,
+                  float *out, ptrdiff_t ldo, int *err_flag, cudaStream_t stream, rb_status *status)
+{
+    const int M = (int)cb.M, k = (int)cb.k, dsub = (int)cb.dsub;
+    *status = RB_OK;
+    if (code_width != 1 || ccs != 1 || crs != (ptrdiff_t)M || (dsub & 1) || M > 4096) return false;
+    if ((reinterpret_cast<uintptr_t>(out) & 15) || (ldo & 3) || (reinterpret_cast<uintptr_t>(codes) & 15)) return false;
+    if ((reinterpret_cast<uintptr_t>(cb.quantizers) & 15) || n < 256) return false;
+    const size_t per_m = (size_t)k * dsub * sizeof(float);
+    const size_t smem_budget = 113 * 1024;  // two 512-thread blocks per SM
+    const size_t cb_budget = 100 * 1024;
+    const int step = (dsub % 4 == 0) ? 1 : 2;  // group width must be a multiple of 4 floats
+    int mg = (int)(cb_budget / per_m);
+    mg -= mg % step;
+    if (mg < step) return false;
+    if (mg > M) mg = M;
+    int n_groups = (int)ceil_div(M, mg);
+    mg = (int)ceil_div(M, n_groups);
+    mg += (step - mg % step) % step;
+    n_groups = (int)ceil_div(M, mg);
+    if (((M - (n_groups - 1) * mg) * dsub) % 4 != 0) return false;  // last group's width
+    if ((size_t)mg * k * dsub % 4 != 0) return false;
+    const size_t cb_bytes = (size_t)mg * per_m;
+    const size_t tab_bytes = (size_t)(mg * dsub / 4) * sizeof(PieceSrc);
+    if (cb_bytes + tab_bytes + 16 * (size_t)M > smem_budget) return false;
+    size_t code_bytes = smem_budget - cb_bytes - tab_bytes;
+    if (code_bytes > (size_t)kTileThreads * kTileVpt * 16) code_bytes = (size_t)kTileThreads * kTileVpt * 16;
+    int tile_rows = (int)(code_bytes / M);
+    tile_rows -= tile_rows % 16;
+    if (tile_rows > 512) tile_rows = 512;
+    if (tile_rows < 16) return false;
+    const size_t smem = cb_bytes + tab_bytes + (size_t)tile_rows * M;
+
+    const long long n_tiles = (long long)ceil_div(n, (size_t)tile_rows);
+    long long strips = (2 * 148) / n_groups;  // one resident wave
+    if (strips < 1) strips = 1;
+    if (strips > n_tiles) strips = n_tiles;
+    const long long tiles_per_strip = (n_tiles + strips - 1) / strips;
+    strips = (n_tiles + tiles_per_strip - 1) / tiles_per_strip;
+    const unsigned grid = (unsigned)(strips * n_groups);
+
+    const bool quad = dsub % 4 == 0, check = k < 256;
+    auto kern = quad ? (check ? gather_tile_kernel<true, true> : gather_tile_kernel<true, false>)
+                     : (check ? gather_tile_kernel<false, true> : gather_tile_kernel<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        *status = RB_ERR_CUDA;
+        return true;
+    }
+    kern<<<grid, kTileThreads, smem, stream>>>(cb.quantizers, k, dsub, M, reinterpret_cast<const uint8_t *>(codes),
+                                              (long long)n, out, (long long)ldo, mg, n_groups, tile_rows,
+                                              tiles_per_strip, (int)(cb_bytes / sizeof(float)), err_flag);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);
+        *status = RB_ERR_CUDA;
+    }
+    return true;
+}
+
 template <int PW>
 rb_status launch_pw(const DeviceCodebook &cb, const void *codes, int code_width, size_t n, ptrdiff_t crs,
                     ptrdiff_t ccs, float *out, ptrdiff_t ldo, int *err_flag, cudaStream_t stream)
@@ -189,6 +388,8 @@ rb_status launch_gather(const DeviceCodebook &cb, const void *codes, int code_wi
                         ptrdiff_t ccs, float *out, ptrdiff_t ldo, int *err_flag, cudaStream_t stream)
 {
     if (n == 0) return RB_OK;
+    rb_status st = RB_OK;
+    if (launch_tiled(cb, codes, code_width, n, crs, ccs, out, ldo, err_flag, stream, &st)) return st;
     if (cb.dsub % 4 == 0) return launch_pw<4>(cb, codes, code_width, n, crs, ccs, out, ldo, err_flag, stream);
     if (cb.dsub % 2 == 0) return launch_pw<2>(cb, codes, code_width, n, crs, ccs, out, ldo, err_flag, stream);
     return launch_pw<1>(cb, codes, code_width, n, crs, ccs, out, ldo, err_flag, stream);
