@@ -15,6 +15,7 @@
 // (up to 32 wavefronts); it walks its strip with a grid-stride loop.  When even one subquantizer's
 // slice does not fit in shared memory the block reads centroids through the read-only path instead.
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace rb {
 
@@ -141,134 +142,141 @@ gather_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, cons
 // Fast path (u8 codes, dense [n, M] code matrix, 16-byte aligned output rows, even dsub): tiled gather.
 //
 // A block owns one column group (a whole number of subquantizers whose width in floats is a multiple of 4; its
-// codebook slice lives in shared memory for the block's lifetime) and walks a strip of row tiles.  Per tile the
-// code bytes of the tile's rows are staged in shared memory by coalesced 16-byte loads that were issued one tile
-// AHEAD (register prefetch), so the inner loop has no global-load latency in it: per 16-byte output piece it
-// reads one or two code bytes and one 16-byte / two 8-byte centroid pieces from shared memory and issues one
-// 16-byte global store.  Consecutive lanes own consecutive pieces of a row, so a warp store writes 512 contiguous
-// bytes (row segments of the group).  Blocks of the column groups of one strip have adjacent block indices: they
-// run concurrently and the 32-byte sectors straddling a group boundary are completed in L2.
+// codebook slice lives in shared memory for the block's lifetime) and walks a strip of row tiles.  The code bytes
+// of a tile's rows are contiguous in global memory; a producer thread streams them through a ring of shared-memory
+// stages with cp.async.bulk (TMA engine) + mbarriers, several tiles ahead, so the consumer warps never wait on a
+// global load and never hit a block-wide barrier in the steady state.  A consumer thread keeps a fixed 16-byte
+// column position (so its centroid offsets are loop-invariant registers) and walks the rows of the tile: per
+// piece it reads one or two code bytes and one 16-byte / two 8-byte centroid pieces from shared memory and issues
+// one 16-byte store.  Consecutive lanes own consecutive pieces of a row -> a warp store writes 512
+// contiguous bytes.  Blocks of the column groups of one strip have adjacent block indices: they run concurrently
+// and the 32-byte sectors straddling a group boundary are completed in L2.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kTileThreads = 512;
-constexpr int kTileVpt = 2;  // 16-byte code vectors prefetched per thread and tile
-
-// piece table entry: where the two 8-byte halves of a 16-byte output piece come from
-struct PieceSrc {
-    uint32_t off0, cc0, off1, cc1;  // float offset into the group's codebook (add code * dsub); code column
-};
+constexpr int kTileConsumers = 512;
+constexpr int kTileThreads = kTileConsumers + 32;  // + the producer warp
+constexpr int kTileStages = 4;
 
 template <bool QUAD, bool CHECK>
 __global__ void __launch_bounds__(kTileThreads, 2)
 gather_tile_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, const uint8_t *__restrict__ codes,
                    long long n, float *__restrict__ out, long long ldo, int m_per_group, int n_groups,
-                   int tile_rows, long long tiles_per_strip, int cb_floats_max, int *__restrict__ err_flag)
+                   int tile_rows, long long tiles_per_strip, int cb_floats_max, int *__restrict__ err_flag, int lockstep)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using namespace ptx;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int g = blockIdx.x % n_groups;
     const long long strip = blockIdx.x / n_groups;
     const int m0 = g * m_per_group;
     const int mg = min(m_per_group, M - m0);
-    const int w4 = mg * dsub / 4;  // 16-byte pieces per row in this group
+    const int w4 = mg * dsub / 4;  // 16-byte pieces per row in this group (<= kTileConsumers)
 
-    float *cb = reinterpret_cast<float *>(smem_raw);                       // [mg][k][dsub]
-    PieceSrc *tab = reinterpret_cast<PieceSrc *>(cb + cb_floats_max);      // [w4]
-    uint8_t *sc = reinterpret_cast<uint8_t *>(tab + (m_per_group * dsub / 4));  // [tile_rows][M]
+    float *cb = reinterpret_cast<float *>(smem_raw);                 // [mg][k][dsub]
+    uint8_t *ring = reinterpret_cast<uint8_t *>(cb + cb_floats_max);  // [kTileStages][tile_rows * M]
+    const int stage_bytes = tile_rows * M;                            // multiple of 16
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kTileStages * stage_bytes);
+    uint64_t *empty = full + kTileStages;
 
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTileStages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kTileConsumers / 32);
+        }
+        fence_mbar_init();
+    }
     {
         const float4 *src = reinterpret_cast<const float4 *>(quantizers + (size_t)m0 * k * dsub);
         float4 *dst = reinterpret_cast<float4 *>(cb);
         const int total4 = mg * k * dsub / 4;
         for (int i = threadIdx.x; i < total4; i += kTileThreads) dst[i] = __ldg(src + i);
-        for (int c4 = threadIdx.x; c4 < w4; c4 += kTileThreads) {
-            PieceSrc e;
-            const int col0 = 4 * c4, col1 = 4 * c4 + 2;
-            e.cc0 = col0 / dsub;
-            e.off0 = e.cc0 * k * dsub + col0 % dsub;
-            e.cc1 = col1 / dsub;
-            e.off1 = e.cc1 * k * dsub + col1 % dsub;
-            tab[c4] = e;
-        }
     }
+    __syncthreads();
 
-    const long long tile0 = strip * tiles_per_strip;
     const long long n_tiles = (n + tile_rows - 1) / tile_rows;
+    const long long tile0 = strip * tiles_per_strip;
     const long long tile1 = min(n_tiles, tile0 + tiles_per_strip);
     const size_t total_code_bytes = (size_t)n * M;
-    const int tile_vecs = tile_rows * M / 16;  // tile_rows * M is a multiple of 16 by construction
 
-    // register prefetch of a tile's code bytes (vectors past the end of the code matrix are skipped; a ragged
-    // last vector is read bytewise)
-    uint4 pre[kTileVpt];
-    auto prefetch = [&](long long tile) {
-        const size_t base = (size_t)tile * tile_rows * M;
-#pragma unroll
-        for (int v = 0; v < kTileVpt; v++) {
-            const int vi = threadIdx.x + v * kTileThreads;
-            const size_t byte0 = base + (size_t)vi * 16;
-            pre[v] = make_uint4(0u, 0u, 0u, 0u);
-            if (vi < tile_vecs && byte0 < total_code_bytes) {
-                if (byte0 + 16 <= total_code_bytes) {
-                    pre[v] = __ldcs(reinterpret_cast<const uint4 *>(codes + byte0));
-                } else {
-                    uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                    for (int b = 0; b < 16; b++)
-                        if (byte0 + b < total_code_bytes) w[b >> 2] |= (uint32_t)codes[byte0 + b] << (8 * (b & 3));
-                    pre[v] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
+    if (warp == kTileConsumers / 32) {
+        // ===================== producer =====================
+        // keeps kTileStages tiles in flight; in lockstep mode the whole warp also takes part in the per-tile
+        // cluster barrier (every thread of the cluster must arrive)
+        auto issue = [&](long long tile, uint32_t it) {
+            const int s = (int)(it % kTileStages);
+            mbar_wait(&empty[s], ((it / kTileStages) & 1) ^ 1);
+            const size_t byte0 = (size_t)tile * stage_bytes;
+            const size_t avail = total_code_bytes - byte0;
+            const uint32_t bytes = (uint32_t)(avail < (size_t)stage_bytes ? avail : (size_t)stage_bytes);
+            const uint32_t bulk = bytes & ~15u;
+            uint8_t *dst = ring + (size_t)s * stage_bytes;
+            for (uint32_t b = bulk; b < bytes; b++) dst[b] = codes[byte0 + b];  // ragged end of the matrix
+            if (bulk) {
+                mbar_arrive_expect_tx(&full[s], bulk);
+                bulk_g2s(dst, codes + byte0, bulk, &full[s]);
+            } else {
+                mbar_arrive(&full[s]);
             }
+        };
+        if (lane == 0)
+            for (long long tile = tile0; tile < min(tile1, tile0 + kTileStages); tile++) issue(tile, (uint32_t)(tile - tile0));
+        for (long long tile = tile0; tile < tile1; tile++) {
+            __syncwarp();
+            if (lockstep) cluster_sync();
+            if (lane == 0 && tile + kTileStages < tile1) issue(tile + kTileStages, (uint32_t)(tile + kTileStages - tile0));
         }
-    };
+        return;
+    }
 
-    const int d_row = kTileThreads / w4, d_c = kTileThreads % w4;
-    const int gcol0 = m0 * dsub;
+    // ===================== consumers =====================
+    const int rows_par = kTileConsumers / w4;
+    const int rl = (int)threadIdx.x / w4, c4 = (int)threadIdx.x % w4;
+    const bool active = rl < rows_par;
+    // where this thread's two 8-byte halves come from (loop invariant)
+    const int col0 = 4 * c4, col1 = 4 * c4 + 2;
+    const int cc0 = col0 / dsub, cc1 = col1 / dsub;
+    const float *src0 = cb + cc0 * k * dsub + col0 % dsub;
+    const float *src1 = cb + cc1 * k * dsub + col1 % dsub;
+    float *ocol = out + m0 * dsub + 4 * c4;
     bool bad = false;
 
-    if (tile0 < tile1) prefetch(tile0);
-    for (long long tile = tile0; tile < tile1; tile++) {
-        __syncthreads();  // everyone is done with the previous tile's codes (and, first time, the codebook is in)
-#pragma unroll
-        for (int v = 0; v < kTileVpt; v++) {
-            const int vi = threadIdx.x + v * kTileThreads;
-            if (vi < tile_vecs) reinterpret_cast<uint4 *>(sc)[vi] = pre[v];
-        }
-        __syncthreads();
-        if (tile + 1 < tile1) prefetch(tile + 1);
-
+    uint32_t it = 0;
+    for (long long tile = tile0; tile < tile1; tile++, it++) {
+        const int s = (int)(it % kTileStages);
+        mbar_wait(&full[s], (it / kTileStages) & 1);
         const long long r0 = tile * tile_rows;
         const int rows = (int)min((long long)tile_rows, n - r0);
-        int row = (int)threadIdx.x / w4, c4 = (int)threadIdx.x % w4;
-        float *orow = out + r0 * ldo + gcol0;
-        while (row < rows) {
-            const PieceSrc e = tab[c4];
-            const uint8_t *crow = sc + row * M + m0;
-            float4 v;
-            if constexpr (QUAD) {  // dsub % 4 == 0: the piece lies inside one centroid
-                unsigned c = crow[e.cc0];
-                if constexpr (CHECK) {
-                    bad |= c >= (unsigned)k;
-                    c = min(c, (unsigned)(k - 1));
+        if (active) {
+            const uint8_t *crow = ring + (size_t)s * stage_bytes + m0 + rl * M;
+            float *op = ocol + (r0 + rl) * ldo;
+            const long long ostep = (long long)rows_par * ldo;
+            const int cstep = rows_par * M;
+#pragma unroll 2
+            for (int row = rl; row < rows; row += rows_par, crow += cstep, op += ostep) {
+                float4 v;
+                if constexpr (QUAD) {  // dsub % 4 == 0: the piece lies inside one centroid
+                    unsigned c = crow[cc0];
+                    if constexpr (CHECK) {
+                        bad |= c >= (unsigned)k;
+                        c = min(c, (unsigned)(k - 1));
+                    }
+                    v = *reinterpret_cast<const float4 *>(src0 + c * dsub);
+                } else {
+                    unsigned ca = crow[cc0], cbb = crow[cc1];
+                    if constexpr (CHECK) {
+                        bad |= (ca >= (unsigned)k) | (cbb >= (unsigned)k);
+                        ca = min(ca, (unsigned)(k - 1));
+                        cbb = min(cbb, (unsigned)(k - 1));
+                    }
+                    const float2 lo = *reinterpret_cast<const float2 *>(src0 + ca * dsub);
+                    const float2 hi = *reinterpret_cast<const float2 *>(src1 + cbb * dsub);
+                    v = make_float4(lo.x, lo.y, hi.x, hi.y);
                 }
-                v = *reinterpret_cast<const float4 *>(cb + e.off0 + c * dsub);
-            } else {
-                unsigned ca = crow[e.cc0], cbb = crow[e.cc1];
-                if constexpr (CHECK) {
-                    bad |= (ca >= (unsigned)k) | (cbb >= (unsigned)k);
-                    ca = min(ca, (unsigned)(k - 1));
-                    cbb = min(cbb, (unsigned)(k - 1));
-                }
-                const float2 lo = *reinterpret_cast<const float2 *>(cb + e.off0 + ca * dsub);
-                const float2 hi = *reinterpret_cast<const float2 *>(cb + e.off1 + cbb * dsub);
-                v = make_float4(lo.x, lo.y, hi.x, hi.y);
-            }
-            __stcs(reinterpret_cast<float4 *>(orow + (long long)row * ldo + 4 * c4), v);
-            row += d_row;
-            c4 += d_c;
-            if (c4 >= w4) {
-                c4 -= w4;
-                row++;
+                *reinterpret_cast<float4 *>(op) = v;
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (lockstep) cluster_sync();
     }
     if (bad) atomicExch(err_flag, 1);
 }
@@ -279,14 +287,15 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
 {
     const int M = (int)cb.M, k = (int)cb.k, dsub = (int)cb.dsub;
     *status = RB_OK;
-    if (code_width != 1 || ccs != 1 || crs != (ptrdiff_t)M || (dsub & 1) || M > 4096) return false;
+    if (code_width != 1 || ccs != 1 || crs != (ptrdiff_t)M || (dsub & 1)) return false;
     if ((reinterpret_cast<uintptr_t>(out) & 15) || (ldo & 3) || (reinterpret_cast<uintptr_t>(codes) & 15)) return false;
     if ((reinterpret_cast<uintptr_t>(cb.quantizers) & 15) || n < 256) return false;
     const size_t per_m = (size_t)k * dsub * sizeof(float);
-    const size_t smem_budget = 113 * 1024;  // two 512-thread blocks per SM
+    const size_t smem_budget = 113 * 1024;  // two blocks per SM
     const size_t cb_budget = 100 * 1024;
     const int step = (dsub % 4 == 0) ? 1 : 2;  // group width must be a multiple of 4 floats
     int mg = (int)(cb_budget / per_m);
+    if ((size_t)mg * dsub / 4 > (size_t)kTileConsumers) mg = kTileConsumers * 4 / dsub;  // one 16-byte piece per thread
     mg -= mg % step;
     if (mg < step) return false;
     if (mg > M) mg = M;
@@ -295,25 +304,14 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
     mg += (step - mg % step) % step;
     n_groups = (int)ceil_div(M, mg);
     if (((M - (n_groups - 1) * mg) * dsub) % 4 != 0) return false;  // last group's width
-    if ((size_t)mg * k * dsub % 4 != 0) return false;
+    if ((size_t)mg * k * dsub % 4 != 0 || (size_t)mg * dsub / 4 > (size_t)kTileConsumers) return false;
     const size_t cb_bytes = (size_t)mg * per_m;
-    const size_t tab_bytes = (size_t)(mg * dsub / 4) * sizeof(PieceSrc);
-    if (cb_bytes + tab_bytes + 16 * (size_t)M > smem_budget) return false;
-    size_t code_bytes = smem_budget - cb_bytes - tab_bytes;
-    if (code_bytes > (size_t)kTileThreads * kTileVpt * 16) code_bytes = (size_t)kTileThreads * kTileVpt * 16;
-    int tile_rows = (int)(code_bytes / M);
+    const size_t bar_bytes = 2 * kTileStages * sizeof(uint64_t);
+    if (cb_bytes + bar_bytes + (size_t)kTileStages * 16 * M > smem_budget) return false;
+    int tile_rows = (int)((smem_budget - cb_bytes - bar_bytes) / kTileStages / M);
     tile_rows -= tile_rows % 16;
-    if (tile_rows > 512) tile_rows = 512;
-    if (tile_rows < 16) return false;
-    const size_t smem = cb_bytes + tab_bytes + (size_t)tile_rows * M;
-
-    const long long n_tiles = (long long)ceil_div(n, (size_t)tile_rows);
-    long long strips = (2 * 148) / n_groups;  // one resident wave
-    if (strips < 1) strips = 1;
-    if (strips > n_tiles) strips = n_tiles;
-    const long long tiles_per_strip = (n_tiles + strips - 1) / strips;
-    strips = (n_tiles + tiles_per_strip - 1) / tiles_per_strip;
-    const unsigned grid = (unsigned)(strips * n_groups);
+    if (tile_rows > 256) tile_rows = 256;
+    const size_t smem = cb_bytes + (size_t)kTileStages * tile_rows * M + bar_bytes;
 
     const bool quad = dsub % 4 == 0, check = k < 256;
     auto kern = quad ? (check ? gather_tile_kernel<true, true> : gather_tile_kernel<true, false>)
@@ -324,9 +322,48 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
         *status = RB_ERR_CUDA;
         return true;
     }
-    kern<<<grid, kTileThreads, smem, stream>>>(cb.quantizers, k, dsub, M, reinterpret_cast<const uint8_t *>(codes),
-                                              (long long)n, out, (long long)ldo, mg, n_groups, tile_rows,
-                                              tiles_per_strip, (int)(cb_bytes / sizeof(float)), err_flag);
+    // The column groups of one strip form a thread-block cluster and advance tile by tile in lockstep, so the
+    // stripes of a row region reach L2 within microseconds of each other and leave it as complete lines.  Not
+    // needed when every stripe segment is a whole number of 128-byte lines anyway.
+    const bool lines_aligned = (reinterpret_cast<uintptr_t>(out) % 128 == 0) && (ldo % 32 == 0) && ((mg * dsub) % 32 == 0);
+    const int lockstep = (n_groups > 1 && n_groups <= 8 && !lines_aligned) ? 1 : 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kTileThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = lockstep ? (unsigned)n_groups : 1u;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+
+    // one resident wave: as many strips as clusters (or blocks) fit on the device at once
+    const long long n_tiles = (long long)ceil_div(n, (size_t)tile_rows);
+    long long strips = (2 * 148) / n_groups;
+    if (lockstep) {
+        int max_clusters = 0;
+        cfg.gridDim = dim3((unsigned)(strips * n_groups));
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess && max_clusters > 0 &&
+            max_clusters < strips)
+            strips = max_clusters;
+        (void)cudaGetLastError();
+    }
+    if (strips < 1) strips = 1;
+    if (strips > n_tiles) strips = n_tiles;
+    const long long tiles_per_strip = (n_tiles + strips - 1) / strips;
+    strips = (n_tiles + tiles_per_strip - 1) / tiles_per_strip;
+    const unsigned grid = (unsigned)(strips * n_groups);
+    cfg.gridDim = dim3(grid);
+    e = cudaLaunchKernelEx(&cfg, kern, cb.quantizers, k, dsub, M, reinterpret_cast<const uint8_t *>(codes),
+                           (long long)n, out, (long long)ldo, mg, n_groups, tile_rows, tiles_per_strip,
+                           (int)(cb_bytes / sizeof(float)), err_flag, lockstep);
+    if (e != cudaSuccess) {
+        set_error("cudaLaunchKernelEx failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);
+        *status = RB_ERR_CUDA;
+        return true;
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -53,6 +53,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+// ---- thread-block clusters --------------------------------------------------------------------------------
+// barrier over every thread of every CTA in the cluster (release / acquire)
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- proxies / bulk copies -------------------------------------------------------------------------------
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma / TMA read shared memory through it)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
