@@ -38,6 +38,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "encode_tc.cuh"
 #include "sm100_ptx.cuh"
@@ -150,9 +151,11 @@ __global__ void tc_prepare_kernel(const float *__restrict__ q, const float *__re
 // ---------------------------------------------------------------------------------------------------------
 // the encode kernel
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxGroups = 148;
+
 struct EncParams {
     const float *x;
-    long long n, ldx;
+    long long n;
     const __half *bop;
     const float *consts;  // [M] csmax | scale | scale2 | bad | absmax
     void *codes;
@@ -161,8 +164,10 @@ struct EncParams {
     uint32_t *pairs;
     uint32_t *n_pairs;
     uint32_t max_pairs;
-    int M, gm, n_groups, a_stages;
-    long long n_tiles, items_total, items_per_cta;
+    int M, gm, n_groups, a_stages, pitch_f;
+    long long n_tiles;
+    long long *trace;  // debugging aid (RB_TC_TRACE): per-role clock64 stamps of CTA 0, else nullptr
+    unsigned short cta_start[kMaxGroups + 1];  // CTAs [cta_start[g], cta_start[g+1]) own column group g
 };
 
 __device__ __forceinline__ float fmin3(float a, float b, float c)
@@ -189,22 +194,32 @@ __device__ __forceinline__ float min16(const uint32_t *v)
     return fminf(r0, r1);
 }
 
+// trace slots (units kTraceU0 .. kTraceU0 + kTraceN - 1 of CTA 0): [role][unit][event]
+constexpr int kTraceU0 = 200, kTraceN = 24, kTraceEv = 4;
+#define RB_TRACE(role, unit, ev)                                                                                  \
+    do {                                                                                                            \
+        if (p.trace != nullptr && blockIdx.x == 0 && (unit) >= kTraceU0 && (unit) < kTraceU0 + kTraceN)             \
+            p.trace[((role) * kTraceN + ((unit) - kTraceU0)) * kTraceEv + (ev)] = clock64();                       \
+    } while (0)
+
 template <int DSUB>
-__global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams p, const __grid_constant__ CUtensorMap tmap)
+__global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_constant__ EncParams p,
+                                                                const __grid_constant__ CUtensorMap tmap)
 {
+    static_assert(DSUB % 2 == 0, "the converter packs pairs of elements");
     constexpr int KPAD = kpad_of(DSUB), NCH = KPAD / 8;
     constexpr int A_BYTES = NCH * kTile * 16, B_BYTES = NCH * kCent * 16;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xs_bytes = kTile * p.gm * DSUB * 4;  // one X stage
+    const int xs_bytes = kTile * p.pitch_f * 4;  // one X stage: 128 rows x pitch
     unsigned char *sB = smem;
     unsigned char *sX = sB + (size_t)p.gm * B_BYTES;
     unsigned char *sA = sX + (size_t)kXStages * xs_bytes;
     float *sMarg = reinterpret_cast<float *>(sA + (size_t)p.a_stages * A_BYTES);  // [kMargRing][kTile]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sMarg + kMargRing * kTile);
     uint64_t *x_full = bars, *x_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 8, *acc_full = bars + 12,
-             *acc_empty = bars + 14, *b_full = bars + 16, *b_free = bars + 17, *drain = bars + 18;
+             *acc_empty = bars + 14, *b_full = bars + 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
 
     if (threadIdx.x == 0) {
@@ -219,8 +234,6 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
             mbar_init(&a_empty[i], 1);
         }
         mbar_init(b_full, 1);
-        mbar_init(b_free, 1);
-        mbar_init(drain, 1);
         fence_mbar_init();
     }
     if (warp == kWarpMma) {
@@ -232,32 +245,28 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const long long it0 = (long long)blockIdx.x * p.items_per_cta;
-    const long long it1 = min(p.items_total, it0 + p.items_per_cta);
+    // this CTA's column group g, its rank among the group's CTAs and their number: it encodes the 128-row tiles
+    // rank, rank + stride, ... for the subquantizers [g*gm, g*gm + gm_cur).  The groups of one tile are handled by
+    // different CTAs at about the same time, so partially used 128-byte lines of x are fetched from HBM once.
+    int g = 0;
+    while (g + 1 < p.n_groups && (int)blockIdx.x >= (int)p.cta_start[g + 1]) g++;
+    const long long t_first = (long long)blockIdx.x - p.cta_start[g];
+    const long long t_stride = (long long)p.cta_start[g + 1] - p.cta_start[g];
+    const int gm_cur = min(p.gm, p.M - g * p.gm);
     const int S = p.a_stages;
 
     if (warp == kWarpProducer) {
         // ===================== producer =====================
         if (lane == 0) {
             prefetch_tensormap(&tmap);
-            int cur_g = -1;
-            uint32_t n_loads = 0;
-            long long li = 0;
-            for (long long item = it0; item < it1; item++, li++) {
-                const int g = (int)(item / p.n_tiles);
-                const long long t = item % p.n_tiles;
-                const int gm_cur = min(p.gm, p.M - g * p.gm);
-                if (g != cur_g) {
-                    if (cur_g >= 0) mbar_wait(b_free, (n_loads - 1) & 1);  // every MMA that read the old operands is done
-                    mbar_arrive_expect_tx(b_full, (uint32_t)gm_cur * B_BYTES);
-                    for (int ml = 0; ml < gm_cur; ml++)
-                        bulk_g2s(sB + (size_t)ml * B_BYTES, p.bop + (size_t)(g * p.gm + ml) * (B_BYTES / 2), B_BYTES, b_full);
-                    cur_g = g;
-                    n_loads++;
-                }
+            mbar_arrive_expect_tx(b_full, (uint32_t)gm_cur * B_BYTES);
+            for (int ml = 0; ml < gm_cur; ml++)
+                bulk_g2s(sB + (size_t)ml * B_BYTES, p.bop + (size_t)(g * p.gm + ml) * (B_BYTES / 2), B_BYTES, b_full);
+            uint32_t li = 0;
+            for (long long t = t_first; t < p.n_tiles; t += t_stride, li++) {
                 const int stage = (int)(li & 1);
-                mbar_wait(&x_empty[stage], (uint32_t)(((li >> 1) & 1) ^ 1));
-                // one TMA tile load: box = 128 rows x (gm * dsub) floats; rows / columns outside the matrix arrive as zeros
+                mbar_wait(&x_empty[stage], ((li >> 1) & 1) ^ 1);
+                // one TMA tile load: box = 128 rows x pitch floats; rows / columns outside the matrix arrive as zeros
                 mbar_arrive_expect_tx(&x_full[stage], (uint32_t)xs_bytes);
                 tma_load_2d(sX + (size_t)stage * xs_bytes, &tmap, g * p.gm * DSUB, (int)(t * kTile), &x_full[stage]);
             }
@@ -267,25 +276,16 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = idesc_f16(kTile, kCent, 0);
-            int cur_g = -1;
-            uint32_t n_loads = 0, u = 0, as = 0, aph = 0;
-            for (long long item = it0; item < it1; item++) {
-                const int g = (int)(item / p.n_tiles);
-                const int gm_cur = min(p.gm, p.M - g * p.gm);
-                if (g != cur_g) {
-                    if (cur_g >= 0) {
-                        tc_commit(drain);
-                        mbar_wait(drain, (n_loads - 1) & 1);
-                        mbar_arrive(b_free);
-                    }
-                    mbar_wait(b_full, n_loads & 1);
-                    n_loads++;
-                    cur_g = g;
-                }
+            uint32_t u = 0, as = 0, aph = 0;
+            mbar_wait(b_full, 0);
+            for (long long t = t_first; t < p.n_tiles; t += t_stride) {
                 for (int ml = 0; ml < gm_cur; ml++, u++) {
                     const uint32_t buf = u & 1;
+                    RB_TRACE(0, u, 0);
                     mbar_wait(&a_full[as], aph);
+                    RB_TRACE(0, u, 1);
                     mbar_wait(&acc_empty[buf], ((u >> 1) & 1) ^ 1);
+                    RB_TRACE(0, u, 2);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + (size_t)as * A_BYTES);
                     const uint32_t b_addr = smem_u32(sB + (size_t)ml * B_BYTES);
@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
                     }
                     tc_commit(&a_empty[as]);
                     tc_commit(&acc_full[buf]);
+                    RB_TRACE(0, u, 3);
                     if (++as == (uint32_t)S) {
                         as = 0;
                         aph ^= 1;
@@ -311,72 +312,79 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
         const float scale = p.consts[p.M + 0];
         const float scale2 = p.consts[p.M + 1];
         const bool cb_bad = p.consts[p.M + 2] != 0.f;
-        uint32_t u = 0, as = 0, aph = 0;
-        long long li = 0;
-        for (long long item = it0; item < it1; item++, li++) {
-            const int g = (int)(item / p.n_tiles);
-            const long long t = item % p.n_tiles;
-            const int gm_cur = min(p.gm, p.M - g * p.gm);
+        uint32_t u = 0, as = 0, aph = 0, li = 0;
+        for (long long t = t_first; t < p.n_tiles; t += t_stride, li++) {
             const int stage = (int)(li & 1);
-            const bool valid = t * kTile + row < p.n;
-            mbar_wait(&x_full[stage], (uint32_t)((li >> 1) & 1));
-            const float *xr = reinterpret_cast<const float *>(sX + (size_t)stage * xs_bytes) + (size_t)row * p.gm * DSUB;
-            for (int ml = 0; ml < gm_cur; ml++, u++) {
-                static_assert(DSUB % 2 == 0, "the converter packs pairs of elements");
-                float sv[DSUB];
-                float xs = 0.f, amax = 0.f;
-                {
-                    const float2 *src = reinterpret_cast<const float2 *>(xr + ml * DSUB);
+            mbar_wait(&x_full[stage], (li >> 1) & 1);
+            const float4 *xr = reinterpret_cast<const float4 *>(sX + (size_t)stage * xs_bytes + (size_t)row * p.pitch_f * 4);
+            // two subquantizers at a time: 2*DSUB floats are a whole number of 16-byte vectors, and with a row pitch
+            // that is an odd multiple of 16 bytes the 128-bit loads of a warp are bank-conflict free
+            for (int ml0 = 0; ml0 < gm_cur; ml0 += 2) {
+                float xv[2 * DSUB];
+#pragma unroll
+                for (int q4 = 0; q4 < DSUB / 2; q4++) {
+                    const float4 v = xr[(ml0 * DSUB) / 4 + q4];
+                    xv[4 * q4] = v.x;
+                    xv[4 * q4 + 1] = v.y;
+                    xv[4 * q4 + 2] = v.z;
+                    xv[4 * q4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (ml0 + h >= gm_cur) break;
+                    const float *sub = xv + h * DSUB;
+                    float xs = 0.f;
+                    uint32_t hw[DSUB / 2], lw[DSUB / 2];
 #pragma unroll
                     for (int t2 = 0; t2 < DSUB / 2; t2++) {
-                        float2 v = valid ? src[t2] : make_float2(0.f, 0.f);
-                        xs = fmaf(v.x, v.x, xs);
-                        xs = fmaf(v.y, v.y, xs);
-                        sv[2 * t2] = v.x * scale;
-                        sv[2 * t2 + 1] = v.y * scale;
-                        amax = fmaxf(amax, fmaxf(fabsf(sv[2 * t2]), fabsf(sv[2 * t2 + 1])));
+                        const float a0 = sub[2 * t2], a1 = sub[2 * t2 + 1];
+                        xs = fmaf(a0, a0, xs);
+                        xs = fmaf(a1, a1, xs);
+                        const float s0 = a0 * scale, s1 = a1 * scale;
+                        // two-limb FP16 split, two elements per conversion instruction
+                        const __half2 hh = __floats2half2_rn(s0, s1);
+                        const float2 hf = __half22float2(hh);
+                        const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+                        hw[t2] = *reinterpret_cast<const uint32_t *>(&hh);
+                        lw[t2] = *reinterpret_cast<const uint32_t *>(&ll);
                     }
-                }
-                // two-limb FP16 split, two elements per conversion instruction
-                uint32_t hw[DSUB / 2], lw[DSUB / 2];
+                    // K layout [xh | xh | xl | 1 1 | 0 ...] as 32-bit words (two halves each)
+                    uint32_t w[KPAD / 2];
 #pragma unroll
-                for (int t2 = 0; t2 < DSUB / 2; t2++) {
-                    const __half2 h = __floats2half2_rn(sv[2 * t2], sv[2 * t2 + 1]);
-                    const float2 hf = __half22float2(h);
-                    const __half2 l = __floats2half2_rn(sv[2 * t2] - hf.x, sv[2 * t2 + 1] - hf.y);
-                    hw[t2] = *reinterpret_cast<const uint32_t *>(&h);
-                    lw[t2] = *reinterpret_cast<const uint32_t *>(&l);
-                }
-                // K layout [xh | xh | xl | 1 1 | 0 ...] as 32-bit words (two halves each)
-                uint32_t w[KPAD / 2];
+                    for (int i = 0; i < KPAD / 2; i++) w[i] = 0u;
 #pragma unroll
-                for (int i = 0; i < KPAD / 2; i++) w[i] = 0u;
-#pragma unroll
-                for (int i = 0; i < DSUB / 2; i++) {
-                    w[i] = hw[i];
-                    w[DSUB / 2 + i] = hw[i];
-                    w[DSUB + i] = lw[i];
-                }
-                w[3 * DSUB / 2] = 0x3c003c00u;  // (1.0, 1.0)
-                // NaN in x makes xs NaN, Inf makes it Inf; |x * scale| beyond the FP16 range: decide such rows exactly
-                const bool bad = cb_bad || !(xs < 3.0e38f) || !(amax <= 32768.f);
-                const float csmax = p.consts[g * p.gm + ml];
-                float marg = margin_of(xs, csmax, DSUB) * scale2;
-                if (bad || !(marg < 3.0e38f)) marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
+                    for (int i = 0; i < DSUB / 2; i++) {
+                        w[i] = hw[i];
+                        w[DSUB / 2 + i] = hw[i];
+                        w[DSUB + i] = lw[i];
+                    }
+                    w[3 * DSUB / 2] = 0x3c003c00u;  // (1.0, 1.0)
+                    // NaN in x makes xs NaN, Inf makes it Inf; |x * scale| <= sqrt(xs) * scale must stay inside the
+                    // FP16 range (2^15): decide such rows exactly
+                    const float xs_sc = xs * scale2;
+                    const bool bad = cb_bad || !(xs_sc < 1.0e9f);
+                    const float csmax = p.consts[g * p.gm + ml0 + h];
+                    float marg = margin_of(xs, csmax, DSUB) * scale2;
+                    if (bad || !(marg < 3.0e38f)) marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
 
-                mbar_wait(&a_empty[as], aph ^ 1);
-                unsigned char *a = sA + (size_t)as * A_BYTES;
+                    RB_TRACE(1, u, 0);
+                    mbar_wait(&a_empty[as], aph ^ 1);
+                    RB_TRACE(1, u, 1);
+                    unsigned char *a = sA + (size_t)as * A_BYTES;
 #pragma unroll
-                for (int c8 = 0; c8 < NCH; c8++)
-                    *reinterpret_cast<uint4 *>(a + ((size_t)c8 * kTile + row) * 16) =
-                        make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
-                sMarg[(u % kMargRing) * kTile + row] = marg;
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[as]);
-                if (++as == (uint32_t)S) {
-                    as = 0;
-                    aph ^= 1;
+                    for (int c8 = 0; c8 < NCH; c8++)
+                        *reinterpret_cast<uint4 *>(a + ((size_t)c8 * kTile + row) * 16) =
+                            make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
+                    sMarg[(u % kMargRing) * kTile + row] = marg;
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[as]);
+                    RB_TRACE(1, u, 2);
+                    if (++as == (uint32_t)S) {
+                        as = 0;
+                        aph ^= 1;
+                    }
+                    u++;
                 }
             }
             __syncwarp();
@@ -390,14 +398,13 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * kCent;
         const float INF = __int_as_float(0x7f800000);
         uint32_t u = 0;
-        for (long long item = it0; item < it1; item++) {
-            const int g = (int)(item / p.n_tiles);
-            const long long t = item % p.n_tiles;
-            const int gm_cur = min(p.gm, p.M - g * p.gm);
+        for (long long t = t_first; t < p.n_tiles; t += t_stride) {
             const long long grow = t * kTile + row;
             for (int ml = 0; ml < gm_cur; ml++, u++) {
                 if ((int)(u & 1) != set) continue;
+                RB_TRACE(2 + set, u, 0);
                 mbar_wait(&acc_full[set], (u >> 1) & 1);
+                RB_TRACE(2 + set, u, 1);
                 tc_fence_after();
                 const float marg = sMarg[(u % kMargRing) * kTile + row];
                 float A[16], B[16];
@@ -424,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[set]);
+                RB_TRACE(2 + set, u, 2);
 
                 float m1 = fmin3(B[0], B[1], B[2]);
                 m1 = fmin3(m1, B[3], B[4]);
@@ -433,25 +441,28 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
                 m1 = fmin3(m1, B[11], B[12]);
                 m1 = fmin3(m1, B[13], B[14]);
                 m1 = fminf(m1, B[15]);
-                // count the block / chain minima below m1 + margin and pick up their positions (FMA pipe):
-                // t = sat((thr - v) * 2^40) is 1 for v < thr (by at least one ulp), 0 for v >= thr and for NaN
+                // Which block / chain minima lie below thr = m1 + margin (FMA pipe): t = sat((thr - v) * 2^40) is
+                // exactly 1 for v < thr and exactly 0 for v >= thr or NaN as long as |thr| >= 2^-14 (then thr - v
+                // is zero or at least ulp(thr) >= 2^-37).  acc = sum t_i * (64 + i) lies in [64, 80) iff exactly
+                // one t_i is set, and then names it.
                 const float thr = m1 + marg;
                 const float SC = 1.099511627776e12f;  // 2^40
                 const float thr_sc = thr * SC;
-                float cb = 0.f, ib = 0.f, ca = 0.f, ia = 0.f;
+                float b0 = 0.f, b1 = 0.f, a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float tb = fma_sat(B[i], -SC, thr_sc);
-                    cb += tb;
-                    ib = fmaf(tb, (float)i, ib);
-                    const float ta = fma_sat(A[i], -SC, thr_sc);
-                    ca += ta;
-                    ia = fmaf(ta, (float)i, ia);
+                for (int i = 0; i < 16; i += 2) {
+                    b0 = fmaf(fma_sat(B[i], -SC, thr_sc), (float)(64 + i), b0);
+                    b1 = fmaf(fma_sat(B[i + 1], -SC, thr_sc), (float)(65 + i), b1);
+                    a0 = fmaf(fma_sat(A[i], -SC, thr_sc), (float)(64 + i), a0);
+                    a1 = fmaf(fma_sat(A[i + 1], -SC, thr_sc), (float)(65 + i), a1);
                 }
-                const bool certain = (cb == 1.f) && (ca == 1.f) && (marg == marg) && (fabsf(m1) < 3.0e38f);
+                const float accb = b0 + b1, acca = a0 + a1;
+                // one block and one chain below thr; |thr| large enough for exact t; NaN margins fail the comparisons
+                const bool certain = (fminf(accb, acca) >= 64.f) && (fmaxf(accb, acca) < 80.f) &&
+                                     (fabsf(thr) >= 6.103515625e-5f) && (fabsf(m1) < 3.0e38f);
                 if (grow < p.n) {
                     const int m = g * p.gm + ml;
-                    unsigned code = certain ? (unsigned)((int)ib * 16 + (int)ia) : 0u;
+                    const unsigned code = certain ? (unsigned)(int)fmaf(accb - 64.f, 16.f, acca - 64.f) : 0u;
                     store_code(p.codes, p.code_width, grow * p.crs + (long long)m * p.ccs, code);
                     if (!certain) {
                         const uint32_t slot = atomicAdd(p.n_pairs, 1u);
@@ -461,6 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
                         }
                     }
                 }
+                RB_TRACE(2 + set, u, 3);
             }
         }
     }
@@ -474,28 +486,65 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const EncParams 
 // host side
 // ---------------------------------------------------------------------------------------------------------
 struct Plan {
-    int gm = 0, n_groups = 0, a_stages = 0;
+    int gm = 0, n_groups = 0, a_stages = 0, pitch_f = 0, ctas = 0;
     size_t smem = 0;
+    unsigned short cta_start[kMaxGroups + 1] = {0};
 };
 
-Plan make_plan(size_t M, size_t dsub)
+// Column grouping and CTA allocation.  A CTA keeps the B operands of one group of gm subquantizers in shared
+// memory for its whole life and walks 128-row tiles; groups get CTAs in proportion to their width.  Chosen to
+// minimise the busiest CTA's number of (tile, subquantizer) units.
+Plan make_plan(size_t M, size_t dsub, size_t n_tiles, int sms)
 {
     Plan best;
+    unsigned long long best_span = ~0ull;
     const size_t kpad = (size_t)kpad_of((int)dsub), nch = kpad / 8;
     const size_t a_bytes = nch * kTile * 16, b_bytes = nch * kCent * 16;
-    if ((M * dsub) % 4 != 0) return best;
-    for (size_t gm = M < 8 ? M : 8; gm >= 1; gm--) {
-        if ((gm * dsub) % 4 != 0) continue;
-        for (int stages = 3; stages >= 2; stages--) {
-            const size_t smem = gm * b_bytes + (size_t)kXStages * kTile * gm * dsub * 4 + (size_t)stages * a_bytes +
-                                (size_t)kMargRing * kTile * 4 + 24 * 8;
-            if (smem <= (size_t)kSmemLimit - 1024) {
-                best.gm = (int)gm;
-                best.n_groups = (int)ceil_div(M, gm);
-                best.a_stages = stages;
-                best.smem = smem;
-                return best;
+    if ((M * dsub) % 4 != 0 || (dsub & 1) || n_tiles == 0) return best;
+    for (size_t gm = M < 16 ? M : 16; gm >= 1; gm--) {
+        const size_t n_groups = ceil_div(M, gm);
+        if (n_groups > (size_t)kMaxGroups || n_groups > (size_t)sms) continue;
+        if ((gm * dsub) % 4 != 0 && n_groups > 1) continue;  // TMA box start: 16-byte aligned column offset
+        // smem row pitch: room for ceil(gm/2) pairs of subvectors, an odd number of 16-byte units
+        size_t pitch_b = ((2 * dsub * ceil_div(gm, 2) * 4 + 15) / 16) * 16;
+        if ((pitch_b / 16) % 2 == 0) pitch_b += 16;
+        if (pitch_b / 4 > 256) continue;  // TMA box extent
+        int stages = 0;
+        size_t smem = 0;
+        for (int s = 4; s >= 2 && !stages; s--) {
+            smem = gm * b_bytes + (size_t)kXStages * kTile * pitch_b + (size_t)s * a_bytes + (size_t)kMargRing * kTile * 4 + 24 * 8;
+            if (smem <= (size_t)kSmemLimit - 1024) stages = s;
+        }
+        if (!stages) continue;
+        // greedy CTA allocation: every group gets one, the rest go to whichever group is busiest
+        size_t ctas = (size_t)sms < n_tiles * n_groups ? (size_t)sms : n_tiles * n_groups;
+        unsigned cnt[kMaxGroups];
+        for (size_t g = 0; g < n_groups; g++) cnt[g] = 1;
+        auto width = [&](size_t g) { return g + 1 < n_groups ? gm : M - (n_groups - 1) * gm; };
+        auto load = [&](size_t g) { return (unsigned long long)ceil_div(n_tiles, (size_t)cnt[g]) * width(g); };
+        for (size_t used = n_groups; used < ctas; used++) {
+            size_t arg = 0;
+            for (size_t g = 1; g < n_groups; g++)
+                if (load(g) > load(arg)) arg = g;
+            if (cnt[arg] >= n_tiles) break;
+            cnt[arg]++;
+        }
+        unsigned long long span = 0;
+        for (size_t g = 0; g < n_groups; g++) span = load(g) > span ? load(g) : span;
+        if (span < best_span) {
+            best_span = span;
+            best.gm = (int)gm;
+            best.n_groups = (int)n_groups;
+            best.a_stages = stages;
+            best.pitch_f = (int)(pitch_b / 4);
+            best.smem = smem;
+            unsigned acc = 0;
+            for (size_t g = 0; g < n_groups; g++) {
+                best.cta_start[g] = (unsigned short)acc;
+                acc += cnt[g];
             }
+            best.cta_start[n_groups] = (unsigned short)acc;
+            best.ctas = (int)acc;
         }
     }
     return best;
@@ -534,16 +583,23 @@ rb_status make_x_tensor_map(const float *x, size_t n, size_t d, ptrdiff_t ldx, s
     return RB_OK;
 }
 
+int device_sm_count()
+{
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > kMaxGroups ? kMaxGroups : sms;
+}
+
 template <int DSUB>
 rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const float *x, size_t n, ptrdiff_t ldx, void *codes,
                    int code_width, ptrdiff_t crs, ptrdiff_t ccs, uint32_t *pairs, uint32_t *n_pairs, uint32_t max_pairs,
                    cudaStream_t stream)
 {
-    const Plan plan = make_plan(cb.M, cb.dsub);
+    const size_t n_tiles = ceil_div(n, (size_t)kTile);
+    const Plan plan = make_plan(cb.M, cb.dsub, n_tiles, device_sm_count());
     EncParams p;
     p.x = x;
     p.n = (long long)n;
-    p.ldx = (long long)ldx;
     p.bop = reinterpret_cast<const __half *>(tc.b_tiles);
     p.consts = tc.consts;
     p.codes = codes;
@@ -557,20 +613,42 @@ rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const flo
     p.gm = plan.gm;
     p.n_groups = plan.n_groups;
     p.a_stages = plan.a_stages;
-    p.n_tiles = (long long)ceil_div(n, (size_t)kTile);
-    p.items_total = p.n_tiles * plan.n_groups;
-    int dev = 0, sms = 148;
-    RB_CUDA_TRY(cudaGetDevice(&dev));
-    RB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long long ctas = p.items_total < sms ? p.items_total : sms;
-    p.items_per_cta = (p.items_total + ctas - 1) / ctas;
-    ctas = (p.items_total + p.items_per_cta - 1) / p.items_per_cta;
+    p.pitch_f = plan.pitch_f;
+    p.n_tiles = (long long)n_tiles;
+    p.trace = nullptr;
+    for (int g = 0; g <= kMaxGroups; g++) p.cta_start[g] = plan.cta_start[g < plan.n_groups ? g : plan.n_groups];
     CUtensorMap tmap;
-    RB_TRY(make_x_tensor_map(x, n, cb.M * cb.dsub, ldx, (size_t)plan.gm * cb.dsub, &tmap));
+    RB_TRY(make_x_tensor_map(x, n, cb.M * cb.dsub, ldx, (size_t)plan.pitch_f, &tmap));
     auto kern = encode_tc_kernel<DSUB>;
     RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    kern<<<(unsigned)ctas, kThreads, plan.smem, stream>>>(p, tmap);
+    const bool trace = getenv("RB_TC_TRACE") != nullptr;
+    const size_t trace_len = (size_t)4 * kTraceN * kTraceEv;
+    if (trace) {
+        RB_CUDA_TRY(cudaMalloc(&p.trace, trace_len * sizeof(long long)));
+        RB_CUDA_TRY(cudaMemset(p.trace, 0, trace_len * sizeof(long long)));
+    }
+    kern<<<(unsigned)plan.ctas, kThreads, plan.smem, stream>>>(p, tmap);
     RB_LAUNCH_CHECK();
+    if (trace) {  // debugging aid: clock64 stamps of CTA 0's roles for a window of units, relative to the first
+        std::vector<long long> h(trace_len);
+        RB_CUDA_TRY(cudaStreamSynchronize(stream));
+        RB_CUDA_TRY(cudaMemcpy(h.data(), p.trace, trace_len * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(p.trace);
+        long long t0 = 0;
+        for (long long v : h)
+            if (v && (!t0 || v < t0)) t0 = v;
+        static const char *roles[4] = {"mma : start a_full acc_empty issued", "conv: ready a_empty written -",
+                                       "epi0: start acc_full scanned done", "epi1: start acc_full scanned done"};
+        for (int r = 0; r < 4; r++) {
+            fprintf(stderr, "[rb tc trace] %s\n", roles[r]);
+            for (int u = 0; u < kTraceN; u++) {
+                const long long *e = &h[((size_t)r * kTraceN + u) * kTraceEv];
+                if (!e[0] && !e[1]) continue;
+                fprintf(stderr, "  u=%d: %lld %lld %lld %lld\n", kTraceU0 + u, e[0] ? e[0] - t0 : -1, e[1] ? e[1] - t0 : -1,
+                        e[2] ? e[2] - t0 : -1, e[3] ? e[3] - t0 : -1);
+            }
+        }
+    }
     return RB_OK;
 }
 
@@ -592,7 +670,7 @@ bool dsub_instantiated(size_t dsub)
 bool tensor_path_supported(const DeviceCodebook &cb)
 {
     if (cb.k != (size_t)kCent || !dsub_instantiated(cb.dsub)) return false;
-    return make_plan(cb.M, cb.dsub).gm > 0;
+    return make_plan(cb.M, cb.dsub, 1u << 20, kMaxGroups).gm > 0;
 }
 
 bool tensor_call_supported(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx)
