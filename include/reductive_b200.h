@@ -139,6 +139,15 @@ rb_status rb_kmeans_assign_accumulate(const float *x, size_t n_local, ptrdiff_t 
                                       const float *centroids, size_t n_subquantizers,
                                       size_t n_centroids, size_t subquantizer_dim, float *packed,
                                       void *stream);
+/* Same, but the update_centroids chains CONTINUE from `packed_before` (DEVICE, rb_kmeans_packed_len floats, or
+ * NULL = start from zero): the sums of the rows that precede these n_local rows in the reference's row order.
+ * kmeans.rs:185-189 adds the rows of a cluster sequentially in f32, so passing the running sums from rank to rank
+ * (rank r's rows follow rank r-1's) keeps data-parallel training bit-identical to one sequential pass.  Needs the
+ * ordered update (default) with k <= 256 and subquantizer_dim <= 32; RB_ERR_UNSUPPORTED otherwise. */
+rb_status rb_kmeans_assign_accumulate_from(const float *x, size_t n_local, ptrdiff_t x_row_stride,
+                                           const float *centroids, size_t n_subquantizers, size_t n_centroids,
+                                           size_t subquantizer_dim, const float *packed_before, float *packed,
+                                           void *stream);
 /* Second half (kmeans.rs:191-197 + mean_squared_error kmeans.rs:330-360): divide non-empty clusters,
  * leave empty clusters at zero, write the new centroids and, if loss_or_null != NULL, the per-
  * subquantizer mean squared error of the new centroids under the old assignments (computed from the

@@ -616,8 +616,9 @@ rb_status rb_check_quantizer_invariants(size_t n_subquantizers, uint32_t n_bits,
 
 size_t rb_kmeans_packed_len(size_t M, size_t k, size_t dsub) { return M * k * dsub + M * k + M; }
 
-rb_status rb_kmeans_assign_accumulate(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids, size_t M,
-                                      size_t k, size_t dsub, float *packed, void *stream)
+rb_status rb_kmeans_assign_accumulate_from(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids,
+                                           size_t M, size_t k, size_t dsub, const float *packed_before,
+                                           float *packed, void *stream)
 {
     if (!centroids || !packed || (n_local && !x)) return fail(RB_ERR_INVALID, "NULL argument");
     if (M == 0 || k == 0 || dsub == 0) return fail(RB_ERR_SHAPE, "Cannot cluster instances with zero centroids.");
@@ -627,17 +628,26 @@ rb_status rb_kmeans_assign_accumulate(const float *x, size_t n_local, ptrdiff_t 
     RB_TRY(cs.alloc(M * k * sizeof(float), st));
     RB_TRY(launch_centroid_norms(centroids, M * k, dsub, cs.as<float>(), st));
     const DeviceCodebook cb{centroids, cs.as<float>(), M, k, dsub};
+    // assignments are an internal temporary: kept column-major [M][pitch] so that the tensor kernel's row-per-thread
+    // stores and the per-subquantizer sort both touch contiguous bytes
     const int width = k <= 256 ? 1 : 4;
-    RB_TRY(codes.alloc(n_local * M * width, st));
+    const size_t pitch = (n_local + 15) / 16 * 16 + 16;
+    RB_TRY(codes.alloc(M * pitch * width, st));
     TensorOperands tc;
     if (g_encode_algo.load() != RB_ENCODE_EXACT) RB_TRY(tc.prepare(cb, st));
-    rb_status s = encode_device(cb, &tc, x, n_local, ldx, 0, codes.p, width, (ptrdiff_t)M, 1, st);  // kmeans.rs:319
+    rb_status s = encode_device(cb, &tc, x, n_local, ldx, 0, codes.p, width, 1, (ptrdiff_t)pitch, st);  // kmeans.rs:319
     if (s == RB_OK)
         s = launch_kmeans_accumulate(x, n_local, ldx, width == 1 ? codes.as<uint8_t>() : nullptr,
-                                     width == 4 ? codes.as<uint32_t>() : nullptr, M, k, dsub, packed,
-                                     g_kmeans_ordered.load(), st);
+                                     width == 4 ? codes.as<uint32_t>() : nullptr, pitch, M, k, dsub, packed_before,
+                                     packed, g_kmeans_ordered.load(), st);
     tc.release_async(st);
     return s;
+}
+
+rb_status rb_kmeans_assign_accumulate(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids, size_t M,
+                                      size_t k, size_t dsub, float *packed, void *stream)
+{
+    return rb_kmeans_assign_accumulate_from(x, n_local, ldx, centroids, M, k, dsub, nullptr, packed, stream);
 }
 
 rb_status rb_kmeans_finalize(const float *packed, size_t M, size_t k, size_t dsub, uint64_t n_total, float *centroids,

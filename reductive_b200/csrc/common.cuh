@@ -188,9 +188,11 @@ rb_status launch_project(const float *x, size_t n, size_t d, ptrdiff_t rsx, ptrd
                          int transpose_r, float *out, cudaStream_t stream);
 
 // kmeans.cu
+// codes: column-major [M][code_pitch] (code_pitch >= n, multiple of 16).  init (or nullptr): packed sums of the rows
+// that precede these in the reference's row order (ordered update only) — the chains continue from them.
 rb_status launch_kmeans_accumulate(const float *x, size_t n, ptrdiff_t ldx, const uint8_t *codes8,
-                                   const uint32_t *codes32, size_t M, size_t k, size_t dsub, float *packed,
-                                   int ordered, cudaStream_t stream);
+                                   const uint32_t *codes32, size_t code_pitch, size_t M, size_t k, size_t dsub,
+                                   const float *init, float *packed, int ordered, cudaStream_t stream);
 rb_status launch_kmeans_finalize(const float *packed, size_t M, size_t k, size_t dsub, uint64_t n_total,
                                  float *centroids, float *loss, cudaStream_t stream);
 

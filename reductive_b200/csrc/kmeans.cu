@@ -36,8 +36,8 @@ constexpr int kAccThreads = 256;
 
 template <bool SMEM_ACC, typename CodeT>
 __global__ void __launch_bounds__(kAccThreads)
-accumulate_kernel(const float *__restrict__ x, long long n, long long ldx, const CodeT *__restrict__ codes, int M,
-                  int k, int dsub, float *__restrict__ packed, long long rows_per_block)
+accumulate_kernel(const float *__restrict__ x, long long n, long long ldx, const CodeT *__restrict__ codes,
+                  long long code_pitch, int M, int k, int dsub, float *__restrict__ packed, long long rows_per_block)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = blockIdx.y;
@@ -66,7 +66,7 @@ accumulate_kernel(const float *__restrict__ x, long long n, long long ldx, const
     if (rl < rows_par) {
         for (int t = dsub <= kAccThreads ? (int)threadIdx.x % dsub : (int)threadIdx.x; t < dsub; t += t_step) {
             for (long long row = r0 + rl; row < r1; row += rows_par) {
-                const int code = (int)codes[row * M + m];
+                const int code = (int)codes[(long long)m * code_pitch + row];
                 const float v = __ldg(x + row * ldx + (long long)m * dsub + t);
                 sq += (double)v * (double)v;
                 if constexpr (SMEM_ACC) {
@@ -114,8 +114,8 @@ constexpr int kSortWarps = 4;  // warps per block; each warp owns one (row chunk
 // Pass 1: per (chunk, m) histogram of codes.  cnt layout [chunk][m][k].
 template <typename CodeT>
 __global__ void __launch_bounds__(kSortWarps * 32)
-sort_hist_kernel(const CodeT *__restrict__ codes, long long n, int M, int k, long long rows_per_chunk, int n_chunks,
-                 unsigned *__restrict__ cnt)
+sort_hist_kernel(const CodeT *__restrict__ codes, long long code_pitch, long long n, int M, int k,
+                 long long rows_per_chunk, int n_chunks, unsigned *__restrict__ cnt)
 {
     extern __shared__ unsigned sh[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -126,7 +126,7 @@ sort_hist_kernel(const CodeT *__restrict__ codes, long long n, int M, int k, lon
     if (pair < (long long)n_chunks * M) {
         const int chunk = (int)(pair / M), m = (int)(pair % M);
         const long long r0 = (long long)chunk * rows_per_chunk, r1 = min(n, r0 + rows_per_chunk);
-        for (long long row = r0 + lane; row < r1; row += 32) atomicAdd(h + (unsigned)codes[row * M + m], 1u);
+        for (long long row = r0 + lane; row < r1; row += 32) atomicAdd(h + (unsigned)codes[(long long)m * code_pitch + row], 1u);
         __syncwarp();
         unsigned *dst = cnt + (size_t)pair * k;
         for (int i = lane; i < k; i += 32) dst[i] = h[i];
@@ -163,8 +163,9 @@ __global__ void sort_scan_kernel(unsigned *__restrict__ cnt, int M, int k, int n
 // list[m][base[m][j] .. + total[m][j]) in increasing row order.
 template <typename CodeT>
 __global__ void __launch_bounds__(kSortWarps * 32)
-sort_scatter_kernel(const CodeT *__restrict__ codes, long long n, int M, int k, long long rows_per_chunk, int n_chunks,
-                    const unsigned *__restrict__ off, const unsigned *__restrict__ base, unsigned *__restrict__ list)
+sort_scatter_kernel(const CodeT *__restrict__ codes, long long code_pitch, long long n, int M, int k,
+                    long long rows_per_chunk, int n_chunks, const unsigned *__restrict__ off,
+                    const unsigned *__restrict__ base, unsigned *__restrict__ list)
 {
     extern __shared__ unsigned sh[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -179,7 +180,7 @@ sort_scatter_kernel(const CodeT *__restrict__ codes, long long n, int M, int k, 
     for (long long rb = r0; rb < r1; rb += 32) {
         const long long row = rb + lane;
         const bool live = row < r1;
-        const unsigned code = live ? (unsigned)codes[row * M + m] : 0xffffffffu;
+        const unsigned code = live ? (unsigned)codes[(long long)m * code_pitch + row] : 0xffffffffu;
         const unsigned peers = __match_any_sync(0xffffffffu, code);  // lanes (= consecutive rows) with my code
         if (live) {
             const unsigned rank = __popc(peers & ((1u << lane) - 1u));
@@ -244,6 +245,235 @@ ordered_sum_kernel(const float *__restrict__ x, long long ldx, long long n, int 
     }
 }
 
+
+// ---- ordered path, fast variant (u8 codes, k <= 256, dsub <= 32) --------------------------------------------
+// Same result as the generic ordered path, organised for the memory system:
+//   sort_local_kernel  one block per (chunk of 4 096 - 65 536 rows, subquantizer): stable counting sort of the chunk's row
+//     offsets by code entirely in shared memory (histogram with shared atomics; stable placement with warp-sequential
+//     steps whose same-code groups come from 8 ballots, one per code bit), written out as one contiguous, fully
+//     coalesced u16 segment plus the k+1 cluster boundaries of the chunk;
+//   ordered_chain_kernel  launched once per chunk, one warp per (subquantizer, cluster): 32 rows per batch — 32 row
+//     gathers in flight (lanes = row slot x component), then the reference's sequential f32 adds (kmeans.rs:185-189)
+//     replayed through shuffles; the running sums live in `packed` between launches.  Because every chain is in
+//     the same chunk at the same time, the chunk's rows (< 96 MB, inside L2) are fetched from HBM once although
+//     each (row, subquantizer) piece is gathered by a different warp.  `init` (or nullptr) continues chains started
+//     on another rank: data-parallel training can pass the running sums from rank to rank and stay bit-identical.
+constexpr int kLocalThreads = 512;
+constexpr int kLocalWarps = kLocalThreads / 32;
+
+// rows per chunk: a power of two in [4096, 65536] (u16 offsets) whose x rows (4*d bytes each) stay below ~96 MB of L2
+int chunk_rows_for(size_t d)
+{
+    size_t rows = ((size_t)96 << 20) / (4 * (d ? d : 1));
+    int p = 4096;
+    while (p < 65536 && (size_t)(2 * p) <= rows) p *= 2;
+    return p;
+}
+
+// lanes holding the same 8-bit code as this lane (what __match_any_sync computes, which is far slower)
+__device__ __forceinline__ unsigned same_code_lanes(unsigned code, bool live)
+{
+    unsigned peers = __ballot_sync(0xffffffffu, live);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const unsigned v = __ballot_sync(0xffffffffu, (code >> b) & 1u);
+        peers &= ((code >> b) & 1u) ? v : ~v;
+    }
+    return peers;
+}
+
+__global__ void __launch_bounds__(kLocalThreads)
+sort_local_kernel(const uint8_t *__restrict__ codes, long long code_pitch, long long n, int M, int k, int n_chunks,
+                  int kChunkRows, uint16_t *__restrict__ list, uint32_t *__restrict__ lstart)
+{
+    const int kRowsPerWarp = kChunkRows / kLocalWarps;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint8_t *sc = sm_raw;                                                   // [kChunkRows] codes of the chunk
+    uint16_t *sorted = reinterpret_cast<uint16_t *>(sm_raw + kChunkRows);   // [kChunkRows] row offsets by code
+    uint32_t *wcnt = reinterpret_cast<uint32_t *>(sorted + kChunkRows);     // [kLocalWarps][k]
+    uint32_t *cstart = wcnt + kLocalWarps * k;                              // [k + 1]
+    const int chunk = blockIdx.x, m = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r0 = (long long)chunk * kChunkRows;
+    const int rows = (int)min((long long)kChunkRows, n - r0);
+    const uint8_t *col = codes + (long long)m * code_pitch + r0;  // 16-byte aligned (pitch and chunk are multiples of 16)
+
+    for (int i = threadIdx.x * 16; i < rows; i += kLocalThreads * 16)
+        *reinterpret_cast<uint4 *>(sc + i) = __ldg(reinterpret_cast<const uint4 *>(col + i));  // pitch padding covers the tail
+    for (int i = threadIdx.x; i < kLocalWarps * k; i += kLocalThreads) wcnt[i] = 0;
+    __syncthreads();
+
+    // pass 1: per-warp histograms (warp w owns rows [w * kRowsPerWarp, (w + 1) * kRowsPerWarp))
+    uint32_t *mine = wcnt + warp * k;
+    const int w0 = warp * kRowsPerWarp;
+    for (int s = 0; s < kRowsPerWarp; s += 32) {
+        const int i = w0 + s + lane;
+        if (i < rows) atomicAdd(mine + sc[i], 1u);
+    }
+    __syncthreads();
+    // exclusive scan over warps per cluster, then over clusters
+    for (int j = threadIdx.x; j < k; j += kLocalThreads) {
+        unsigned run = 0;
+        for (int w = 0; w < kLocalWarps; w++) {
+            const unsigned c = wcnt[w * k + j];
+            wcnt[w * k + j] = run;
+            run += c;
+        }
+        cstart[j + 1] = run;  // cluster total for now
+    }
+    __syncthreads();
+    if (warp == 0) {  // k <= 256 totals: a few per lane, then a warp scan
+        const int per = (k + 31) / 32;
+        unsigned local = 0;
+        for (int q = 0; q < per; q++) {
+            const int j = lane * per + q;
+            if (j < k) local += cstart[j + 1];
+        }
+        unsigned incl = local;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
+        }
+        unsigned run = incl - local;
+        for (int q = 0; q < per; q++) {
+            const int j = lane * per + q;
+            if (j < k) {
+                run += cstart[j + 1];
+                cstart[j + 1] = run;  // END of cluster j == start of cluster j + 1
+            }
+        }
+        if (lane == 0) cstart[0] = 0;
+    }
+    __syncthreads();
+    // pass 2: stable placement (rows of a warp in order, lanes of a step in order)
+    for (int s = 0; s < kRowsPerWarp; s += 32) {
+        const int i = w0 + s + lane;
+        const bool live = i < rows;
+        const unsigned code = live ? sc[i] : 0u;
+        const unsigned peers = same_code_lanes(code, live);
+        if (live) {
+            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            sorted[cstart[code] + mine[code] + rank] = (uint16_t)i;
+        }
+        __syncwarp();
+        if (live && (peers >> lane) == 1u) mine[code] += __popc(peers);  // highest lane of the group advances
+        __syncwarp();
+    }
+    __syncthreads();
+    uint16_t *dst = list + ((size_t)m * n_chunks + chunk) * kChunkRows;
+    for (int i = threadIdx.x * 8; i < rows; i += kLocalThreads * 8)
+        *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(sorted + i);
+    uint32_t *ls = lstart + ((size_t)chunk * M + m) * (k + 1);
+    for (int j = threadIdx.x; j <= k; j += kLocalThreads) ls[j] = cstart[j];
+}
+
+template <int DSUB>
+__global__ void __launch_bounds__(256)
+ordered_chain_kernel(const float *__restrict__ x, long long ldx, int M, int k, int n_chunks, int chunk, int kChunkRows,
+                     const uint16_t *__restrict__ list, const uint32_t *__restrict__ lstart,
+                     const float *__restrict__ init, float *__restrict__ packed)
+{
+    constexpr int R = 32 / DSUB;            // row slots per gather instruction
+    constexpr int U = (32 + R - 1) / R;     // gather instructions per batch of 32 rows
+    const int lane = threadIdx.x & 31;
+    const long long mj = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (mj >= (long long)M * k) return;  // whole warp
+    const int m = (int)(mj / k), j = (int)(mj % k);
+    const int r = lane / DSUB, t = lane % DSUB;
+    const bool lane_on = r < R;
+    const long long chains = (long long)M * k * DSUB;
+    const float *xc = x + (long long)m * DSUB + t;
+    // the chain so far: other ranks' rows (init) before this rank's first chunk, else what the last launch left
+    const float *prev = chunk == 0 ? init : packed;
+    float acc = prev ? prev[mj * DSUB + t] : 0.f;
+    double sq = 0.0;
+    const uint32_t *ls = lstart + ((size_t)chunk * M + m) * (k + 1) + j;
+    const unsigned s = __ldg(ls), e = __ldg(ls + 1);
+    const uint16_t *seg = list + ((size_t)m * n_chunks + chunk) * kChunkRows;
+    const long long row_base = (long long)chunk * kChunkRows;
+    for (unsigned i = s; i < e; i += 32) {
+        const int cnt = (int)min(32u, e - i);
+        const unsigned off_l = lane < cnt ? (unsigned)__ldg(seg + i + lane) : 0u;
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int slot = u * R + r;
+            const unsigned off = __shfl_sync(0xffffffffu, off_l, slot & 31);
+            const bool valid = lane_on && slot < cnt;
+            v[u] = valid ? __ldg(xc + (row_base + off) * ldx) : 0.f;
+            sq += (double)v[u] * (double)v[u];
+        }
+        // the reference's chain: rows in increasing order, one rounded add each
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int rr = 0; rr < R; rr++) {
+                const int slot = u * R + rr;
+                const float vv = __shfl_sync(0xffffffffu, v[u], (rr * DSUB + t) & 31);
+                if (slot < cnt) acc = __fadd_rn(acc, vv);
+            }
+        }
+    }
+    if (lane < DSUB) packed[mj * DSUB + t] = acc;
+    if (lane == 0) packed[chains + mj] = (prev ? prev[chains + mj] : 0.f) + (float)(e - s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if (lane == 0 && sq != 0.0) atomicAdd(packed + chains + (long long)M * k + m, (float)sq);
+}
+
+bool fast_ordered_supported(size_t n, size_t k, size_t dsub)
+{
+    if (k > 256 || n >= ((size_t)1 << 40)) return false;
+    switch (dsub) {
+    case 1: case 2: case 4: case 8: case 16: case 32: case 3: case 5: case 6: case 10: case 12: case 15: case 20: case 30:
+        return true;
+    default: return false;
+    }
+}
+
+rb_status launch_ordered_fast(const float *x, size_t n, ptrdiff_t ldx, const uint8_t *codes, size_t code_pitch, size_t M,
+                              size_t k, size_t dsub, const float *init, float *packed, cudaStream_t stream)
+{
+    const int kChunkRows = chunk_rows_for(M * dsub);
+    const size_t n_chunks = ceil_div(n, (size_t)kChunkRows);
+    uint16_t *list = nullptr;
+    uint32_t *lstart = nullptr;
+    RB_CUDA_TRY(cudaMallocAsync(&list, M * n_chunks * kChunkRows * sizeof(uint16_t), stream));
+    RB_CUDA_TRY(cudaMallocAsync(&lstart, n_chunks * M * (k + 1) * sizeof(uint32_t), stream));
+    rb_status st = RB_OK;
+    auto body = [&]() -> rb_status {
+        const size_t smem = kChunkRows + (size_t)kChunkRows * 2 + (size_t)kLocalWarps * k * 4 + (k + 1) * 4;
+        RB_CUDA_TRY(cudaFuncSetAttribute(sort_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sort_local_kernel<<<dim3((unsigned)n_chunks, (unsigned)M), kLocalThreads, smem, stream>>>(
+            codes, (long long)code_pitch, (long long)n, (int)M, (int)k, (int)n_chunks, kChunkRows, list, lstart);
+        RB_LAUNCH_CHECK();
+        if (init) {  // the sum of squared norms continues as well
+            RB_CUDA_TRY(cudaMemcpyAsync(packed + M * k * dsub + M * k, init + M * k * dsub + M * k, M * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, stream));
+        }
+        const unsigned blocks = (unsigned)ceil_div(M * k, 8);
+        for (size_t c = 0; c < n_chunks; c++) {
+#define RB_CHAIN(D)                                                                                                  \
+    case D:                                                                                                          \
+        ordered_chain_kernel<D><<<blocks, 256, 0, stream>>>(x, (long long)ldx, (int)M, (int)k, (int)n_chunks, (int)c, \
+                                                            kChunkRows, list, lstart, init, packed);                             \
+        break;
+            switch (dsub) {
+                RB_CHAIN(1) RB_CHAIN(2) RB_CHAIN(3) RB_CHAIN(4) RB_CHAIN(5) RB_CHAIN(6) RB_CHAIN(8) RB_CHAIN(10)
+                RB_CHAIN(12) RB_CHAIN(15) RB_CHAIN(16) RB_CHAIN(20) RB_CHAIN(30) RB_CHAIN(32)
+            default: break;
+            }
+            RB_LAUNCH_CHECK();
+        }
+        return RB_OK;
+    };
+    st = body();
+    cudaFreeAsync(list, stream);
+    cudaFreeAsync(lstart, stream);
+    return st;
+}
+
 __global__ void __launch_bounds__(256)
 finalize_kernel(const float *__restrict__ packed, int M, int k, int dsub, double inv_len, float *__restrict__ centroids,
                 float *__restrict__ loss)
@@ -280,8 +510,8 @@ finalize_kernel(const float *__restrict__ packed, int M, int k, int dsub, double
 }
 
 template <typename CodeT>
-rb_status launch_acc_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT *codes, size_t M, size_t k, size_t dsub,
-                       float *packed, cudaStream_t stream)
+rb_status launch_acc_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT *codes, size_t code_pitch, size_t M, size_t k,
+                       size_t dsub, float *packed, cudaStream_t stream)
 {
     const size_t pad = dsub | 1;
     const size_t smem = k * pad * sizeof(float) + k * sizeof(int);
@@ -296,11 +526,12 @@ rb_status launch_acc_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT *cod
         auto kern = accumulate_kernel<true, CodeT>;
         if (smem > 48 * 1024)
             RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kAccThreads, smem, stream>>>(x, (long long)n, (long long)ldx, codes, (int)M, (int)k, (int)dsub,
-                                                 packed, (long long)rows_per_block);
+        kern<<<grid, kAccThreads, smem, stream>>>(x, (long long)n, (long long)ldx, codes, (long long)code_pitch, (int)M,
+                                                 (int)k, (int)dsub, packed, (long long)rows_per_block);
     } else {
         accumulate_kernel<false, CodeT><<<grid, kAccThreads, 0, stream>>>(
-            x, (long long)n, (long long)ldx, codes, (int)M, (int)k, (int)dsub, packed, (long long)rows_per_block);
+            x, (long long)n, (long long)ldx, codes, (long long)code_pitch, (int)M, (int)k, (int)dsub, packed,
+            (long long)rows_per_block);
     }
     RB_LAUNCH_CHECK();
     return RB_OK;
@@ -308,8 +539,8 @@ rb_status launch_acc_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT *cod
 
 
 template <typename CodeT>
-rb_status launch_ordered_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT *codes, size_t M, size_t k, size_t dsub,
-                           float *packed, cudaStream_t stream)
+rb_status launch_ordered_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT *codes, size_t code_pitch, size_t M, size_t k,
+                           size_t dsub, float *packed, cudaStream_t stream)
 {
     // chunks: about 2 waves of warps over the GPU, at least 256 rows per chunk
     size_t n_chunks = ceil_div((size_t)148 * 64, M);
@@ -326,13 +557,14 @@ rb_status launch_ordered_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT 
     const unsigned blocks = (unsigned)ceil_div(pairs, kSortWarps);
     rb_status st = RB_OK;
     auto body = [&]() -> rb_status {
-        sort_hist_kernel<CodeT><<<blocks, kSortWarps * 32, smem, stream>>>(codes, (long long)n, (int)M, (int)k,
-                                                                          (long long)rows_per_chunk, (int)n_chunks, cnt);
+        sort_hist_kernel<CodeT><<<blocks, kSortWarps * 32, smem, stream>>>(
+            codes, (long long)code_pitch, (long long)n, (int)M, (int)k, (long long)rows_per_chunk, (int)n_chunks, cnt);
         RB_LAUNCH_CHECK();
         sort_scan_kernel<<<(unsigned)M, 256, 0, stream>>>(cnt, (int)M, (int)k, (int)n_chunks, total, base);
         RB_LAUNCH_CHECK();
         sort_scatter_kernel<CodeT><<<blocks, kSortWarps * 32, smem, stream>>>(
-            codes, (long long)n, (int)M, (int)k, (long long)rows_per_chunk, (int)n_chunks, cnt, base, list);
+            codes, (long long)code_pitch, (long long)n, (int)M, (int)k, (long long)rows_per_chunk, (int)n_chunks, cnt, base,
+            list);
         RB_LAUNCH_CHECK();
         const size_t chains = M * k * dsub;
         ordered_sum_kernel<<<(unsigned)ceil_div(chains, 256), 256, 0, stream>>>(
@@ -351,17 +583,28 @@ rb_status launch_ordered_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT 
 }  // namespace
 
 rb_status launch_kmeans_accumulate(const float *x, size_t n, ptrdiff_t ldx, const uint8_t *codes8,
-                                   const uint32_t *codes32, size_t M, size_t k, size_t dsub, float *packed,
-                                   int ordered, cudaStream_t stream)
+                                   const uint32_t *codes32, size_t code_pitch, size_t M, size_t k, size_t dsub,
+                                   const float *init, float *packed, int ordered, cudaStream_t stream)
 {
-    RB_CUDA_TRY(cudaMemsetAsync(packed, 0, rb_kmeans_packed_len(M, k, dsub) * sizeof(float), stream));
-    if (n == 0) return RB_OK;
-    if (ordered && k <= 1024 && n < ((size_t)1 << 32)) {
-        if (codes8) return launch_ordered_t<uint8_t>(x, n, ldx, codes8, M, k, dsub, packed, stream);
-        return launch_ordered_t<uint32_t>(x, n, ldx, codes32, M, k, dsub, packed, stream);
+    const size_t len = rb_kmeans_packed_len(M, k, dsub);
+    if (init && !(ordered && codes8 && fast_ordered_supported(n, k, dsub))) {
+        set_error("continuing chains (init) needs the ordered update with u8 codes (k <= 256, dsub <= 32)");
+        return RB_ERR_UNSUPPORTED;
     }
-    if (codes8) return launch_acc_t<uint8_t>(x, n, ldx, codes8, M, k, dsub, packed, stream);
-    return launch_acc_t<uint32_t>(x, n, ldx, codes32, M, k, dsub, packed, stream);
+    if (n == 0) {
+        if (init) RB_CUDA_TRY(cudaMemcpyAsync(packed, init, len * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        else RB_CUDA_TRY(cudaMemsetAsync(packed, 0, len * sizeof(float), stream));
+        return RB_OK;
+    }
+    RB_CUDA_TRY(cudaMemsetAsync(packed, 0, len * sizeof(float), stream));
+    if (ordered && codes8 && fast_ordered_supported(n, k, dsub))
+        return launch_ordered_fast(x, n, ldx, codes8, code_pitch, M, k, dsub, init, packed, stream);
+    if (ordered && k <= 1024 && n < ((size_t)1 << 32)) {
+        if (codes8) return launch_ordered_t<uint8_t>(x, n, ldx, codes8, code_pitch, M, k, dsub, packed, stream);
+        return launch_ordered_t<uint32_t>(x, n, ldx, codes32, code_pitch, M, k, dsub, packed, stream);
+    }
+    if (codes8) return launch_acc_t<uint8_t>(x, n, ldx, codes8, code_pitch, M, k, dsub, packed, stream);
+    return launch_acc_t<uint32_t>(x, n, ldx, codes32, code_pitch, M, k, dsub, packed, stream);
 }
 
 rb_status launch_kmeans_finalize(const float *packed, size_t M, size_t k, size_t dsub, uint64_t n_total,
