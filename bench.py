@@ -30,6 +30,8 @@ METRIC = "quantize_batch_vectors_per_s"
 UNIT = "vectors/s"
 N_ROWS, M, K_CENTROIDS, DSUB = 2_000_000, 30, 256, 10
 D = M * DSUB
+# dram__bytes_read.sum + dram__bytes_write.sum of encode_tc_kernel<10> on this workload (ncu --set full, v5)
+ENCODE_DRAM_BYTES_PER_LAUNCH = 2.4346e9 + 0.0612e9
 WORKLOAD = "C2: quantize_batch 2M x 300 f32 N(0,1), 30 subquantizers x 256 centroids, u8 codes"
 
 
@@ -43,53 +45,57 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region.  The timed region is tens of milliseconds, so the
+    sampler polls NVML directly (every ~1 ms) from a thread; `nvidia-smi -lms` (B200_PROFILING.md's clocks line)
+    cannot start that fast and is only the fallback."""
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.samples, self.reasons, self.mx = gpu_index, [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            self.ready.set()
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.001)
+        except Exception as e:  # noqa: BLE001 - reported in the JSON line
+            self.err = repr(e)
+            self.ready.set()
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.ready = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        self.ready.wait(timeout=10)
+        self.samples.clear()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [s.strip() for s in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "samples": 0,
+                    "reasons": ["clock sampling unavailable: " + str(self.err)]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.mx, "samples": len(self.samples),
+                "reasons": sorted(self.reasons)}
 
 
 def _codebook(seed=1):
@@ -254,8 +260,21 @@ def run_ours(args) -> None:
     if world > 1:
         dist.all_reduce(tk, op=dist.ReduceOp.MAX)
     extra["pq_kmeans"] = {"workload": f"C3: 1M x 768 f32, 96 x 256 centroids, rows sharded over {world} GPU(s)",
-                          "sec_per_iter": float(tk.item()) * 1e-3, "iters_timed": iters3,
-                          "allreduce_bytes_per_iter": 4 * (M3 * K_CENTROIDS * (dsub3 + 1) + M3) if world > 1 else 0}
+                          "sec_per_iter": float(tk.item()) * 1e-3, "iters_timed": iters3, "mode": "allreduce",
+                          "allreduce_bytes_per_iter": 4 * (M3 * K_CENTROIDS * (dsub3 + 1) + M3) if world > 1 else 0,
+                          "parity": "bit-identical to the oracle on 1 GPU; with >1 GPU the all-reduce changes the "
+                                    "summation order (centroids drift ~1e-3 after 10 iterations, loss ~1e-6)"}
+    if world > 1:  # chained mode: running sums relayed rank to rank, bit-identical to a one-GPU run
+        kmeans_data_parallel(x3, n3, cen3, 1, mode="chained")
+        barrier()
+        k0.record(stream)
+        kmeans_data_parallel(x3, n3, cen3, iters3, mode="chained")
+        k1.record(stream)
+        barrier()
+        tk = torch.tensor([k0.elapsed_time(k1) / iters3], device=dev, dtype=torch.float64)
+        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        extra["pq_kmeans_chained"] = {"sec_per_iter": float(tk.item()) * 1e-3, "iters_timed": iters3,
+                                      "parity": "bit-identical to the one-GPU run and the oracle"}
     del x3
 
     if rank == 0:
@@ -268,7 +287,9 @@ def run_ours(args) -> None:
         achieved = N_ROWS * bytes_per_vec / (kern_ms * 1e-3) / 1e9
         tflops = N_ROWS * flops_per_vec / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": ENCODE_DRAM_BYTES_PER_LAUNCH,
+                    "traffic_source": "profiles/r1_encode_tc_v5_ncu.txt (dram__bytes_read + write, one launch)",
+                    "peak_source": peaks["source"],
                     "kernel_ms": kern_ms, "algorithmic_bytes_per_vector": bytes_per_vec,
                     "tensor_tflops_algorithmic": tflops, "tensor_frac_of_bf16_peak": tflops / peaks["bf16_tflops"],
                     "tensor_frac_of_tf32_half_peak": tflops / (peaks["bf16_tflops"] / 2)}

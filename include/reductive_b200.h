@@ -139,11 +139,26 @@ rb_status rb_kmeans_assign_accumulate(const float *x, size_t n_local, ptrdiff_t 
                                       const float *centroids, size_t n_subquantizers,
                                       size_t n_centroids, size_t subquantizer_dim, float *packed,
                                       void *stream);
-/* Same, but the update_centroids chains CONTINUE from `packed_before` (DEVICE, rb_kmeans_packed_len floats, or
- * NULL = start from zero): the sums of the rows that precede these n_local rows in the reference's row order.
- * kmeans.rs:185-189 adds the rows of a cluster sequentially in f32, so passing the running sums from rank to rank
- * (rank r's rows follow rank r-1's) keeps data-parallel training bit-identical to one sequential pass.  Needs the
- * ordered update (default) with k <= 256 and subquantizer_dim <= 32; RB_ERR_UNSUPPORTED otherwise. */
+/* The two halves of the call above, for callers that overlap or chain them (data-parallel training):
+ *   rb_kmeans_assign      cluster_assignments (kmeans.rs:133-159) of the local rows for all M subquantizers into
+ *                         `codes`: DEVICE, column-major [M][rb_kmeans_code_pitch(n_local)] elements of
+ *                         rb_kmeans_code_width(k) bytes (1 for k <= 256, else 4);
+ *   rb_kmeans_accumulate  the scatter-add of update_centroids (kmeans.rs:181-189) into `packed`, CONTINUING from
+ *                         `packed_before` (DEVICE, rb_kmeans_packed_len floats, or NULL = from zero): the sums of the
+ *                         rows that precede these n_local rows in the reference's row order.  kmeans.rs:185-189 adds
+ *                         the rows of a cluster sequentially in f32, so passing the running sums from rank to rank
+ *                         (rank r's rows follow rank r-1's) keeps data-parallel training bit-identical to one
+ *                         sequential pass.  A non-NULL packed_before needs the ordered update (default) with
+ *                         k <= 256 and subquantizer_dim <= 32; RB_ERR_UNSUPPORTED otherwise. */
+size_t rb_kmeans_code_pitch(size_t n_local);
+int rb_kmeans_code_width(size_t n_centroids);
+rb_status rb_kmeans_assign(const float *x, size_t n_local, ptrdiff_t x_row_stride, const float *centroids,
+                           size_t n_subquantizers, size_t n_centroids, size_t subquantizer_dim, void *codes,
+                           void *stream);
+rb_status rb_kmeans_accumulate(const float *x, size_t n_local, ptrdiff_t x_row_stride, const void *codes,
+                               size_t n_subquantizers, size_t n_centroids, size_t subquantizer_dim,
+                               const float *packed_before, float *packed, void *stream);
+/* rb_kmeans_assign followed by rb_kmeans_accumulate with an internal assignment buffer. */
 rb_status rb_kmeans_assign_accumulate_from(const float *x, size_t n_local, ptrdiff_t x_row_stride,
                                            const float *centroids, size_t n_subquantizers, size_t n_centroids,
                                            size_t subquantizer_dim, const float *packed_before, float *packed,

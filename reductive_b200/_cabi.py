@@ -39,7 +39,8 @@ EXPORTED_SYMBOLS = [
     "rb_pq_n_quantizer_centroids", "rb_pq_has_projection", "rb_pq_subquantizers", "rb_pq_projection",
     "rb_pq_quantize_batch", "rb_pq_quantize_vector", "rb_pq_reconstruct_batch", "rb_pq_reconstruct",
     "rb_check_quantizer_invariants", "rb_kmeans_packed_len", "rb_kmeans_assign_accumulate",
-    "rb_kmeans_assign_accumulate_from",
+    "rb_kmeans_assign_accumulate_from", "rb_kmeans_code_pitch", "rb_kmeans_code_width", "rb_kmeans_assign",
+    "rb_kmeans_accumulate",
     "rb_kmeans_finalize", "rb_pq_train", "rb_project_rows",
 ]
 
@@ -120,6 +121,11 @@ def _load() -> C.CDLL:
     lib.rb_kmeans_packed_len.restype = sz
     lib.rb_kmeans_assign_accumulate.argtypes = [fp, sz, pd, fp, sz, sz, sz, fp, vp]
     lib.rb_kmeans_assign_accumulate_from.argtypes = [fp, sz, pd, fp, sz, sz, sz, fp, fp, vp]
+    lib.rb_kmeans_code_pitch.argtypes = [sz]
+    lib.rb_kmeans_code_pitch.restype = sz
+    lib.rb_kmeans_code_width.argtypes = [sz]
+    lib.rb_kmeans_assign.argtypes = [fp, sz, pd, fp, sz, sz, sz, vp, vp]
+    lib.rb_kmeans_accumulate.argtypes = [fp, sz, pd, vp, sz, sz, sz, fp, fp, vp]
     lib.rb_kmeans_finalize.argtypes = [fp, sz, sz, sz, C.c_uint64, fp, fp, vp]
     lib.rb_pq_train.argtypes = [fp, sz, sz, pd, pd, sz, C.c_uint32, sz, sz, fp, fp, C.c_int, vp, C.POINTER(vp)]
     lib.rb_project_rows.argtypes = [fp, sz, sz, pd, pd, fp, C.c_int, fp, vp]

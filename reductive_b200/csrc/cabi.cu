@@ -616,6 +616,43 @@ rb_status rb_check_quantizer_invariants(size_t n_subquantizers, uint32_t n_bits,
 
 size_t rb_kmeans_packed_len(size_t M, size_t k, size_t dsub) { return M * k * dsub + M * k + M; }
 
+size_t rb_kmeans_code_pitch(size_t n_local) { return (n_local + 15) / 16 * 16 + 16; }
+int rb_kmeans_code_width(size_t k) { return k <= 256 ? 1 : 4; }
+
+rb_status rb_kmeans_assign(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids, size_t M, size_t k,
+                           size_t dsub, void *codes, void *stream)
+{
+    if (!centroids || !codes || (n_local && !x)) return fail(RB_ERR_INVALID, "NULL argument");
+    if (M == 0 || k == 0 || dsub == 0) return fail(RB_ERR_SHAPE, "Cannot cluster instances with zero centroids.");
+    RB_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace cs;
+    RB_TRY(cs.alloc(M * k * sizeof(float), st));
+    RB_TRY(launch_centroid_norms(centroids, M * k, dsub, cs.as<float>(), st));
+    const DeviceCodebook cb{centroids, cs.as<float>(), M, k, dsub};
+    TensorOperands tc;
+    if (g_encode_algo.load() != RB_ENCODE_EXACT) RB_TRY(tc.prepare(cb, st));
+    // column-major [M][pitch]: the tensor kernel's row-per-thread stores and the per-subquantizer sort both touch
+    // contiguous bytes
+    const rb_status s = encode_device(cb, &tc, x, n_local, ldx, 0, codes, rb_kmeans_code_width(k), 1,
+                                      (ptrdiff_t)rb_kmeans_code_pitch(n_local), st);  // kmeans.rs:319
+    tc.release_async(st);
+    return s;
+}
+
+rb_status rb_kmeans_accumulate(const float *x, size_t n_local, ptrdiff_t ldx, const void *codes, size_t M, size_t k,
+                               size_t dsub, const float *packed_before, float *packed, void *stream)
+{
+    if (!codes || !packed || (n_local && !x)) return fail(RB_ERR_INVALID, "NULL argument");
+    if (M == 0 || k == 0 || dsub == 0) return fail(RB_ERR_SHAPE, "Cannot cluster instances with zero centroids.");
+    RB_TRY(require_device());
+    const int width = rb_kmeans_code_width(k);
+    return launch_kmeans_accumulate(x, n_local, ldx, width == 1 ? reinterpret_cast<const uint8_t *>(codes) : nullptr,
+                                    width == 4 ? reinterpret_cast<const uint32_t *>(codes) : nullptr,
+                                    rb_kmeans_code_pitch(n_local), M, k, dsub, packed_before, packed,
+                                    g_kmeans_ordered.load(), (cudaStream_t)stream);
+}
+
 rb_status rb_kmeans_assign_accumulate_from(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids,
                                            size_t M, size_t k, size_t dsub, const float *packed_before,
                                            float *packed, void *stream)
@@ -624,24 +661,10 @@ rb_status rb_kmeans_assign_accumulate_from(const float *x, size_t n_local, ptrdi
     if (M == 0 || k == 0 || dsub == 0) return fail(RB_ERR_SHAPE, "Cannot cluster instances with zero centroids.");
     RB_TRY(require_device());
     cudaStream_t st = (cudaStream_t)stream;
-    Workspace cs, codes;
-    RB_TRY(cs.alloc(M * k * sizeof(float), st));
-    RB_TRY(launch_centroid_norms(centroids, M * k, dsub, cs.as<float>(), st));
-    const DeviceCodebook cb{centroids, cs.as<float>(), M, k, dsub};
-    // assignments are an internal temporary: kept column-major [M][pitch] so that the tensor kernel's row-per-thread
-    // stores and the per-subquantizer sort both touch contiguous bytes
-    const int width = k <= 256 ? 1 : 4;
-    const size_t pitch = (n_local + 15) / 16 * 16 + 16;
-    RB_TRY(codes.alloc(M * pitch * width, st));
-    TensorOperands tc;
-    if (g_encode_algo.load() != RB_ENCODE_EXACT) RB_TRY(tc.prepare(cb, st));
-    rb_status s = encode_device(cb, &tc, x, n_local, ldx, 0, codes.p, width, 1, (ptrdiff_t)pitch, st);  // kmeans.rs:319
-    if (s == RB_OK)
-        s = launch_kmeans_accumulate(x, n_local, ldx, width == 1 ? codes.as<uint8_t>() : nullptr,
-                                     width == 4 ? codes.as<uint32_t>() : nullptr, pitch, M, k, dsub, packed_before,
-                                     packed, g_kmeans_ordered.load(), st);
-    tc.release_async(st);
-    return s;
+    Workspace codes;  // assignments are an internal temporary here
+    RB_TRY(codes.alloc(M * rb_kmeans_code_pitch(n_local) * (size_t)rb_kmeans_code_width(k), st));
+    RB_TRY(rb_kmeans_assign(x, n_local, ldx, centroids, M, k, dsub, codes.p, stream));
+    return rb_kmeans_accumulate(x, n_local, ldx, codes.p, M, k, dsub, packed_before, packed, stream);
 }
 
 rb_status rb_kmeans_assign_accumulate(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids, size_t M,

@@ -9,7 +9,10 @@
     It restates the loop of kmeans_with_centroids (src/kmeans.rs:263-288) around kmeans_iteration
     (src/kmeans.rs:308-327) for all M subquantizers of Pq::train_pq_using (src/pq/pq.rs:201-249) at once.
 
-`local_step` / `finalize` are injectable so that the sharding + all-reduce logic is testable on CPU with the
+    A second mode ("chained") trades the all-reduce for a rank-to-rank relay of the running sums and is
+    bit-identical to a one-process run (see kmeans_data_parallel).
+
+`local_step` / `assign` / `accumulate` / `finalize` are injectable so that the sharding + all-reduce logic is testable on CPU with the
 gloo backend (tests/test_dist_gloo.py); the defaults call the CUDA library and fail without a GPU.
 """
 from __future__ import annotations
@@ -40,6 +43,30 @@ def cuda_local_step(x_local, centroids, packed) -> None:
                                           torch.cuda.current_stream().cuda_stream))
 
 
+def cuda_assign(x_local, centroids):
+    """cluster_assignments of this rank's rows (src/kmeans.rs:319); returns the device buffer of assignments."""
+    import torch
+
+    M, k, dsub = centroids.shape
+    n = x_local.shape[0]
+    nbytes = M * int(lib.rb_kmeans_code_pitch(n)) * int(lib.rb_kmeans_code_width(k))
+    codes = torch.empty((nbytes,), dtype=torch.uint8, device=x_local.device)
+    check(lib.rb_kmeans_assign(x_local.data_ptr(), n, x_local.stride(0), centroids.data_ptr(), M, k, dsub,
+                               codes.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return codes
+
+
+def cuda_accumulate(x_local, centroids, codes, packed_before, packed) -> None:
+    """update_centroids' scatter-add of this rank's rows, continuing the chains of the preceding ranks
+    (src/kmeans.rs:181-189)."""
+    import torch
+
+    M, k, dsub = centroids.shape
+    check(lib.rb_kmeans_accumulate(x_local.data_ptr(), x_local.shape[0], x_local.stride(0), codes.data_ptr(), M, k, dsub,
+                                   None if packed_before is None else packed_before.data_ptr(), packed.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream))
+
+
 def cuda_finalize(packed, n_total: int, centroids, loss) -> None:
     """divide / zero empties / loss on the all-reduced sums (src/kmeans.rs:191-197, 330-360)."""
     import torch
@@ -51,24 +78,54 @@ def cuda_finalize(packed, n_total: int, centroids, loss) -> None:
 
 def kmeans_data_parallel(x_local, n_total: int, centroids, n_iterations: int, group=None,
                          local_step: Optional[Callable] = None, finalize: Optional[Callable] = None,
-                         on_iteration: Optional[Callable] = None):
+                         on_iteration: Optional[Callable] = None, mode: str = "allreduce",
+                         assign: Optional[Callable] = None, accumulate: Optional[Callable] = None):
     """Run `n_iterations` data-parallel Lloyd iterations IN PLACE on `centroids` ([M,k,dsub], identical on every
     rank); returns the per-subquantizer loss of the last iteration ([M] tensor).
 
-    x_local: this rank's rows [n_local, d] (d = M*dsub, unit column stride)."""
+    x_local: this rank's rows [n_local, d] (d = M*dsub, unit column stride); rank r holds the rows that follow
+    rank r-1's in the global row order (shard_rows).
+
+    mode "allreduce" (BASELINE config C3): ONE all-reduce(sum) of the packed per-rank sums per iteration.  The
+      per-cluster sums are then added in a different order than the reference's single sequential f32 chain
+      (src/kmeans.rs:185-189); k-means amplifies such last-bit differences (a flipped near-tie moves two
+      centroids), so trained centroids agree with a one-process run only to ~1e-3 relative after ~10 iterations
+      at n = 1M, although the loss agrees to ~1e-6.
+    mode "chained": every rank assigns its rows in parallel, then the running sums travel rank 0 -> 1 -> ... ->
+      last (point-to-point) with each rank CONTINUING the chains over its rows, and the last rank broadcasts the
+      totals.  The update is serialised across ranks but the result is bit-identical to one sequential pass —
+      the oracle's and the reference's — for any number of GPUs."""
     import torch
     import torch.distributed as dist
 
     local_step = local_step or cuda_local_step
     finalize = finalize or cuda_finalize
+    assign = assign or cuda_assign
+    accumulate = accumulate or cuda_accumulate
+    if mode not in ("allreduce", "chained"):
+        raise ValueError(f"unknown mode {mode!r}")
     M, k, dsub = centroids.shape
-    packed = torch.empty((M * k * dsub + M * k + M,), dtype=torch.float32, device=centroids.device)
+    plen = M * k * dsub + M * k + M
+    packed = torch.empty((plen,), dtype=torch.float32, device=centroids.device)
     loss = torch.zeros((M,), dtype=torch.float32, device=centroids.device)
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if distributed and mode == "chained":
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+        before = torch.empty((plen,), dtype=torch.float32, device=centroids.device) if rank > 0 else None
     for it in range(n_iterations):
-        local_step(x_local, centroids, packed)
-        if distributed:
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)  # the one exchange per iteration
+        if distributed and mode == "chained":
+            codes = assign(x_local, centroids)                       # all ranks at once
+            if rank > 0:
+                dist.recv(before, src=ranks[rank - 1], group=group)  # sums over the rows of ranks < rank
+            accumulate(x_local, centroids, codes, before, packed)
+            if rank + 1 < world:
+                dist.send(packed, dst=ranks[rank + 1], group=group)
+            dist.broadcast(packed, src=ranks[world - 1], group=group)
+        else:
+            local_step(x_local, centroids, packed)
+            if distributed:
+                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)  # the one exchange per iteration
         finalize(packed, n_total, centroids, loss)
         if on_iteration is not None:
             on_iteration(it)

@@ -85,3 +85,82 @@ def test_data_parallel_kmeans_world2_matches_single_process(oracle):
     want_q, want_loss = oracle.train_pq(x, M, 3, iters, 1, init)
     assert np.linalg.norm(cen - want_q) / np.linalg.norm(want_q) < 1e-4
     assert np.allclose(loss, want_loss, rtol=1e-3)
+
+
+# ---- chained mode: the running sums travel rank to rank, result bit-identical to one sequential pass -------------
+def _np_assign(o):
+    def assign(x_local, centroids):
+        M, k, dsub = centroids.shape
+        x, c = x_local.numpy(), centroids.numpy()
+        return [o.cluster_assignments(c[m], np.ascontiguousarray(x[:, m * dsub:(m + 1) * dsub])).astype(np.int64)
+                for m in range(M)]
+    return assign
+
+
+def _np_accumulate(x_local, centroids, codes, before, packed):
+    """kmeans.rs:185-189 restated: one rounded f32 add per row, in row order, continuing from `before`."""
+    M, k, dsub = centroids.shape
+    x = x_local.numpy()
+    n0 = M * k * dsub
+    flat = np.zeros((n0 + M * k + M,), np.float32) if before is None else before.numpy().copy()
+    sums, counts, sq = flat[:n0].reshape(M, k, dsub), flat[n0:n0 + M * k].reshape(M, k), flat[n0 + M * k:]
+    for m in range(M):
+        sub = x[:, m * dsub:(m + 1) * dsub]
+        for i, a in enumerate(codes[m]):
+            sums[m, a] = sums[m, a] + sub[i]  # float32 + float32, rounded once
+            counts[m, a] += np.float32(1)
+        sq[m] = np.float32(np.float64(sq[m]) + (sub.astype(np.float64) ** 2).sum())
+    packed.copy_(torch.from_numpy(flat))
+
+
+def _np_finalize_f32(packed, n_total, centroids, loss):
+    """kmeans.rs:191-197 in f32: centroid /= count for non-empty clusters, empty ones stay zero."""
+    M, k, dsub = centroids.shape
+    p = packed.numpy()
+    n0 = M * k * dsub
+    sums, counts = p[:n0].reshape(M, k, dsub), p[n0:n0 + M * k].reshape(M, k)
+    c = np.zeros_like(sums)
+    nz = counts > 0
+    c[nz] = sums[nz] / counts[nz][:, None]
+    centroids.copy_(torch.from_numpy(c))
+
+
+def _chained_worker(rank, world, port, n, M, k, dsub, iters, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from reductive_b200.dist import kmeans_data_parallel, shard_rows
+
+    o = orc.get()
+    x = normal((n, M * dsub), 31)
+    init = rows_as_initial_centroids(x, M, k, 32)[0]
+    lo, hi = shard_rows(n, rank, world)
+    cen = torch.from_numpy(init.copy())
+    kmeans_data_parallel(torch.from_numpy(x[lo:hi]), n, cen, iters, mode="chained", assign=_np_assign(o),
+                         accumulate=_np_accumulate, finalize=_np_finalize_f32)
+    q.put((rank, cen.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_chained_data_parallel_kmeans_is_bit_identical_to_one_process(oracle, world):
+    n, M, k, dsub, iters = 500, 2, 8, 4, 5
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_chained_worker, args=(r, world, port, n, M, k, dsub, iters, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x = normal((n, M * dsub), 31)
+    init = rows_as_initial_centroids(x, M, k, 32)
+    want_q, _ = oracle.train_pq(x, M, 3, iters, 1, init)
+    for r in range(world):  # replicated and bit-identical to the oracle's sequential k-means
+        assert np.array_equal(got[r].view(np.uint32), want_q.view(np.uint32)), r

@@ -366,3 +366,35 @@ def test_k_means_3():  # kmeans.rs:459-479
 
     cen, _ = rb.KMeans.k_means(x, 3, OnePerBlob(), rb.NIterationsCondition(10))
     assert sorted(map(tuple, np.rint(cen).astype(int).tolist())) == [(0, 0), (1, 0), (1, 1)]
+
+
+def test_chained_accumulate_equals_one_pass(oracle, torch_cuda):
+    """rb_kmeans_assign + rb_kmeans_accumulate with packed_before: the chains of a second block of rows continue the
+    first block's sums, so a split pass is bit-identical to one pass and to the oracle (kmeans.rs:185-189).  Sizes
+    straddle the sort chunk (32 768 rows at d = 40) so several chunks and a ragged tail are covered."""
+    torch = torch_cuda
+    from reductive_b200.dist import cuda_accumulate, cuda_assign, cuda_finalize, cuda_local_step
+
+    n, M, k, dsub = 70_001, 5, 64, 8
+    x = normal((n, M * dsub), 101)
+    init = rows_as_initial_centroids(x, M, k, 102)[0]
+    xd = torch.from_numpy(x).cuda()
+    cen = torch.from_numpy(init.copy()).cuda()
+    plen = M * k * dsub + M * k + M
+    one = torch.empty((plen,), dtype=torch.float32, device="cuda")
+    cuda_local_step(xd, cen, one)
+    n0 = M * k * dsub + M * k  # sums and counts (the sum of squared norms is accumulated with float atomics)
+    for cut in (1, 33_000, 65_536, n - 1):
+        a, b = xd[:cut], xd[cut:]
+        p0 = torch.empty_like(one)
+        p1 = torch.empty_like(one)
+        cuda_accumulate(a, cen, cuda_assign(a, cen), None, p0)
+        cuda_accumulate(b, cen, cuda_assign(b, cen), p0, p1)
+        assert torch.equal(p1[:n0].view(torch.int32), one[:n0].view(torch.int32)), cut
+        assert torch.allclose(p1[n0:], one[n0:], rtol=1e-5)
+    # and the finalized centroids are the oracle's
+    loss = torch.zeros((M,), device="cuda")
+    cuda_finalize(one, n, cen, loss)
+    want = np.stack([oracle.kmeans_iteration(np.ascontiguousarray(x[:, m * dsub:(m + 1) * dsub]), init[m])[0]
+                     for m in range(M)])
+    assert np.array_equal(cen.cpu().numpy().view(np.uint32), want.view(np.uint32))
