@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libreductive_b200.so")
+# RB_LIB_PATH: development aid for A/B runs of two builds of the same library (never a different backend)
+LIB_PATH = os.environ.get("RB_LIB_PATH") or os.path.join(_HERE, "lib", "libreductive_b200.so")
 
 # rb_status
 OK = 0

@@ -54,8 +54,10 @@ constexpr int kCent = 256;   // centroids (UMMA N)
 constexpr int kXStages = 2;
 constexpr int kMargRing = 8;
 constexpr int kThreads = 32 * 14;
-// Warp roles.  The SM's warp arbiter favours higher warp ids, so the roles every other warp waits on (producer, MMA
-// issuer, converters) sit above the eight epilogue warps (whose TMEM lane quarter is warp % 4).
+// Warp roles: 8 epilogue warps (TMEM lane quarter = warp % 4), 4 converter warps, the MMA issuer and the TMA producer.
+// Measured with the RB_TC_TRACE phase profile: the SM sub-partition that hosts the MMA-issuing warp scans ~35 % slower
+// than the other three (560 vs 410 clocks per unit) and sets the pace; rotating the issue duty over converter warps or
+// over two / four issuer warps did not pay off, so the single issuer stays.
 constexpr int kWarpConv0 = 8, kWarpMma = 12, kWarpProducer = 13;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -194,12 +196,21 @@ __device__ __forceinline__ float min16(const uint32_t *v)
     return fminf(r0, r1);
 }
 
-// trace slots (units kTraceU0 .. kTraceU0 + kTraceN - 1 of CTA 0): [role][unit][event]
-constexpr int kTraceU0 = 200, kTraceN = 24, kTraceEv = 4;
-#define RB_TRACE(role, unit, ev)                                                                                  \
-    do {                                                                                                            \
-        if (p.trace != nullptr && blockIdx.x == 0 && (unit) >= kTraceU0 && (unit) < kTraceU0 + kTraceN)             \
-            p.trace[((role) * kTraceN + ((unit) - kTraceU0)) * kTraceEv + (ev)] = clock64();                       \
+// Phase profile (RB_TC_TRACE): every warp's lane 0 of CTA 0 accumulates clock() deltas per phase in registers and
+// writes them once at the end: trace[warp * 8 + phase].  Phase meanings are per role (see the host-side dump).
+#define RB_PH_BEGIN() unsigned ph_t = clock(); unsigned long long ph_acc[6] = {0, 0, 0, 0, 0, 0}; (void)ph_t; (void)ph_acc
+#define RB_PH(i)                                   \
+    do {                                           \
+        if (p.trace != nullptr) {                  \
+            const unsigned now_ = clock();         \
+            ph_acc[i] += (unsigned)(now_ - ph_t);  \
+            ph_t = now_;                           \
+        }                                          \
+    } while (0)
+#define RB_PH_END()                                                                                       \
+    do {                                                                                                  \
+        if (p.trace != nullptr && blockIdx.x == 0 && lane == 0)                                           \
+            for (int i_ = 0; i_ < 6; i_++) p.trace[warp * 8 + i_] = (long long)ph_acc[i_];                \
     } while (0)
 
 template <int DSUB>
@@ -275,35 +286,45 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
     } else if (warp == kWarpMma) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
+            // This single thread sits on the critical path between an accumulator being released and the next
+            // scan starting, so its per-unit instruction stream is kept minimal: the shared-memory descriptors
+            // differ only in the 14-bit start-address field of their low word, which is advanced by adds.
             const uint32_t idesc = idesc_f16(kTile, kCent, 0);
-            uint32_t u = 0, as = 0, aph = 0;
+            const uint64_t a_desc0 = smem_desc_kmajor(smem_u32(sA), kTile * 16, 128);
+            const uint64_t b_desc0 = smem_desc_kmajor(smem_u32(sB), kCent * 16, 128);
+            const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
+            constexpr uint32_t A_STEP = A_BYTES >> 4, B_STEP = B_BYTES >> 4;            // per stage / per subquantizer
+            constexpr uint32_t A_KS = (2 * kTile * 16) >> 4, B_KS = (2 * kCent * 16) >> 4;  // per K = 16 slice
+            uint32_t u = 0, as = 0, aph = 0, a_lo = a_lo0;
+            RB_PH_BEGIN();
             mbar_wait(b_full, 0);
             for (long long t = t_first; t < p.n_tiles; t += t_stride) {
-                for (int ml = 0; ml < gm_cur; ml++, u++) {
+                uint32_t b_lo = b_lo0;
+                for (int ml = 0; ml < gm_cur; ml++, u++, b_lo += B_STEP) {
                     const uint32_t buf = u & 1;
-                    RB_TRACE(0, u, 0);
-                    mbar_wait(&a_full[as], aph);
-                    RB_TRACE(0, u, 1);
+                    RB_PH(0);
                     mbar_wait(&acc_empty[buf], ((u >> 1) & 1) ^ 1);
-                    RB_TRACE(0, u, 2);
+                    RB_PH(1);
+                    mbar_wait(&a_full[as], aph);
+                    RB_PH(2);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + (size_t)as * A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + (size_t)ml * B_BYTES);
 #pragma unroll
-                    for (int ks = 0; ks < KPAD / 16; ks++) {
-                        const uint64_t ad = smem_desc_kmajor(a_addr + ks * 2 * kTile * 16, kTile * 16, 128);
-                        const uint64_t bd = smem_desc_kmajor(b_addr + ks * 2 * kCent * 16, kCent * 16, 128);
-                        mma_f16_ss(tmem_base + buf * kCent, ad, bd, idesc, ks > 0 ? 1u : 0u);
-                    }
-                    tc_commit(&a_empty[as]);
+                    for (int ks = 0; ks < KPAD / 16; ks++)
+                        mma_f16_ss_lohi(tmem_base + buf * kCent, a_lo + ks * A_KS, a_hi, b_lo + ks * B_KS, b_hi, idesc,
+                                        ks > 0 ? 1u : 0u);
                     tc_commit(&acc_full[buf]);
-                    RB_TRACE(0, u, 3);
+                    tc_commit(&a_empty[as]);
+                    RB_PH(3);
+                    a_lo += A_STEP;
                     if (++as == (uint32_t)S) {
                         as = 0;
                         aph ^= 1;
+                        a_lo = a_lo0;
                     }
                 }
             }
+            RB_PH_END();
         }
         __syncwarp();
     } else if (warp >= kWarpConv0) {
@@ -313,9 +334,12 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
         const float scale2 = p.consts[p.M + 1];
         const bool cb_bad = p.consts[p.M + 2] != 0.f;
         uint32_t u = 0, as = 0, aph = 0, li = 0;
+        RB_PH_BEGIN();
         for (long long t = t_first; t < p.n_tiles; t += t_stride, li++) {
             const int stage = (int)(li & 1);
+            RB_PH(0);
             mbar_wait(&x_full[stage], (li >> 1) & 1);
+            RB_PH(1);
             const float4 *xr = reinterpret_cast<const float4 *>(sX + (size_t)stage * xs_bytes + (size_t)row * p.pitch_f * 4);
             // two subquantizers at a time: 2*DSUB floats are a whole number of 16-byte vectors, and with a row pitch
             // that is an odd multiple of 16 bytes the 128-bit loads of a warp are bank-conflict free
@@ -366,10 +390,9 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     const float csmax = p.consts[g * p.gm + ml0 + h];
                     float marg = margin_of(xs, csmax, DSUB) * scale2;
                     if (bad || !(marg < 3.0e38f)) marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
-
-                    RB_TRACE(1, u, 0);
+                    RB_PH(2);
                     mbar_wait(&a_empty[as], aph ^ 1);
-                    RB_TRACE(1, u, 1);
+                    RB_PH(3);
                     unsigned char *a = sA + (size_t)as * A_BYTES;
 #pragma unroll
                     for (int c8 = 0; c8 < NCH; c8++)
@@ -379,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[as]);
-                    RB_TRACE(1, u, 2);
+                    RB_PH(4);
                     if (++as == (uint32_t)S) {
                         as = 0;
                         aph ^= 1;
@@ -390,6 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[stage]);
         }
+        RB_PH_END();
     } else {
         // ===================== epilogue (thread = row = TMEM lane) =====================
         const int set = warp >> 2;
@@ -397,16 +421,22 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
         const int row = q * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * kCent;
         const float INF = __int_as_float(0x7f800000);
-        uint32_t u = 0;
-        for (long long t = t_first; t < p.n_tiles; t += t_stride) {
+        // this set's units are u = set, set + 2, ...: (tile, ml) advance by two subquantizers with wrap-around
+        long long t = t_first;
+        int ml = set;
+        while (ml >= gm_cur && t < p.n_tiles) {
+            ml -= gm_cur;
+            t += t_stride;
+        }
+        RB_PH_BEGIN();
+        for (uint32_t u = (uint32_t)set; t < p.n_tiles; u += 2) {
             const long long grow = t * kTile + row;
-            for (int ml = 0; ml < gm_cur; ml++, u++) {
-                if ((int)(u & 1) != set) continue;
-                RB_TRACE(2 + set, u, 0);
+            const int m = g * p.gm + ml;
+            {
+                RB_PH(0);
                 mbar_wait(&acc_full[set], (u >> 1) & 1);
-                RB_TRACE(2 + set, u, 1);
+                RB_PH(1);
                 tc_fence_after();
-                const float marg = sMarg[(u % kMargRing) * kTile + row];
                 float A[16], B[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) A[i] = INF;
@@ -431,37 +461,31 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[set]);
-                RB_TRACE(2 + set, u, 2);
+                RB_PH(2);
+                const float marg = sMarg[(u % kMargRing) * kTile + row];
 
-                float m1 = fmin3(B[0], B[1], B[2]);
-                m1 = fmin3(m1, B[3], B[4]);
-                m1 = fmin3(m1, B[5], B[6]);
-                m1 = fmin3(m1, B[7], B[8]);
-                m1 = fmin3(m1, B[9], B[10]);
-                m1 = fmin3(m1, B[11], B[12]);
-                m1 = fmin3(m1, B[13], B[14]);
-                m1 = fminf(m1, B[15]);
+                // minimum of the 16 block minima as a tree (short dependency chain)
+                const float ma = fmin3(B[0], B[1], B[2]), mb = fmin3(B[3], B[4], B[5]), mc = fmin3(B[6], B[7], B[8]);
+                const float md = fmin3(B[9], B[10], B[11]), me = fmin3(B[12], B[13], B[14]);
+                const float m1 = fminf(fmin3(ma, mb, mc), fmin3(md, me, B[15]));
                 // Which block / chain minima lie below thr = m1 + margin (FMA pipe): t = sat((thr - v) * 2^40) is
                 // exactly 1 for v < thr and exactly 0 for v >= thr or NaN as long as |thr| >= 2^-14 (then thr - v
                 // is zero or at least ulp(thr) >= 2^-37).  acc = sum t_i * (64 + i) lies in [64, 80) iff exactly
-                // one t_i is set, and then names it.
+                // one t_i is set, and then names it.  Four partial sums each keep the dependency chains short.
                 const float thr = m1 + marg;
                 const float SC = 1.099511627776e12f;  // 2^40
                 const float thr_sc = thr * SC;
-                float b0 = 0.f, b1 = 0.f, a0 = 0.f, a1 = 0.f;
+                float bs[4] = {0.f, 0.f, 0.f, 0.f}, as4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    b0 = fmaf(fma_sat(B[i], -SC, thr_sc), (float)(64 + i), b0);
-                    b1 = fmaf(fma_sat(B[i + 1], -SC, thr_sc), (float)(65 + i), b1);
-                    a0 = fmaf(fma_sat(A[i], -SC, thr_sc), (float)(64 + i), a0);
-                    a1 = fmaf(fma_sat(A[i + 1], -SC, thr_sc), (float)(65 + i), a1);
+                for (int i = 0; i < 16; i++) {
+                    bs[i & 3] = fmaf(fma_sat(B[i], -SC, thr_sc), (float)(64 + i), bs[i & 3]);
+                    as4[i & 3] = fmaf(fma_sat(A[i], -SC, thr_sc), (float)(64 + i), as4[i & 3]);
                 }
-                const float accb = b0 + b1, acca = a0 + a1;
+                const float accb = (bs[0] + bs[1]) + (bs[2] + bs[3]), acca = (as4[0] + as4[1]) + (as4[2] + as4[3]);
                 // one block and one chain below thr; |thr| large enough for exact t; NaN margins fail the comparisons
                 const bool certain = (fminf(accb, acca) >= 64.f) && (fmaxf(accb, acca) < 80.f) &&
                                      (fabsf(thr) >= 6.103515625e-5f) && (fabsf(m1) < 3.0e38f);
                 if (grow < p.n) {
-                    const int m = g * p.gm + ml;
                     const unsigned code = certain ? (unsigned)(int)fmaf(accb - 64.f, 16.f, acca - 64.f) : 0u;
                     store_code(p.codes, p.code_width, grow * p.crs + (long long)m * p.ccs, code);
                     if (!certain) {
@@ -472,9 +496,15 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                         }
                     }
                 }
-                RB_TRACE(2 + set, u, 3);
+                RB_PH(3);
+            }
+            ml += 2;
+            while (ml >= gm_cur && t < p.n_tiles) {
+                ml -= gm_cur;
+                t += t_stride;
             }
         }
+        RB_PH_END();
     }
 
     tc_fence_before();
@@ -622,31 +652,28 @@ rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const flo
     auto kern = encode_tc_kernel<DSUB>;
     RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     const bool trace = getenv("RB_TC_TRACE") != nullptr;
-    const size_t trace_len = (size_t)4 * kTraceN * kTraceEv;
+    const size_t trace_len = (size_t)(kThreads / 32) * 8;
     if (trace) {
         RB_CUDA_TRY(cudaMalloc(&p.trace, trace_len * sizeof(long long)));
         RB_CUDA_TRY(cudaMemset(p.trace, 0, trace_len * sizeof(long long)));
     }
     kern<<<(unsigned)plan.ctas, kThreads, plan.smem, stream>>>(p, tmap);
     RB_LAUNCH_CHECK();
-    if (trace) {  // debugging aid: clock64 stamps of CTA 0's roles for a window of units, relative to the first
+    if (trace) {  // debugging aid: where CTA 0's warps spent their clocks, per (tile, subquantizer) unit
         std::vector<long long> h(trace_len);
         RB_CUDA_TRY(cudaStreamSynchronize(stream));
         RB_CUDA_TRY(cudaMemcpy(h.data(), p.trace, trace_len * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(p.trace);
-        long long t0 = 0;
-        for (long long v : h)
-            if (v && (!t0 || v < t0)) t0 = v;
-        static const char *roles[4] = {"mma : start a_full acc_empty issued", "conv: ready a_empty written -",
-                                       "epi0: start acc_full scanned done", "epi1: start acc_full scanned done"};
-        for (int r = 0; r < 4; r++) {
-            fprintf(stderr, "[rb tc trace] %s\n", roles[r]);
-            for (int u = 0; u < kTraceN; u++) {
-                const long long *e = &h[((size_t)r * kTraceN + u) * kTraceEv];
-                if (!e[0] && !e[1]) continue;
-                fprintf(stderr, "  u=%d: %lld %lld %lld %lld\n", kTraceU0 + u, e[0] ? e[0] - t0 : -1, e[1] ? e[1] - t0 : -1,
-                        e[2] ? e[2] - t0 : -1, e[3] ? e[3] - t0 : -1);
-            }
+        const double units = (double)ceil_div(n_tiles, (size_t)(plan.cta_start[1] - plan.cta_start[0])) *
+                             (double)(plan.n_groups > 1 ? plan.gm : (int)cb.M);
+        fprintf(stderr, "[rb tc phases] clocks per unit of CTA 0 (%.0f units)\n", units);
+        fprintf(stderr, "  epilogue: loop | wait acc_full | scan | certificate+store\n");
+        fprintf(stderr, "  converter: loop | wait x_full | load+convert | wait a_empty | write+publish\n");
+        fprintf(stderr, "  mma: loop | wait acc_empty | wait a_full | issue+commit\n");
+        for (int w = 0; w < kThreads / 32; w++) {
+            fprintf(stderr, "  warp %2d:", w);
+            for (int i = 0; i < 6; i++) fprintf(stderr, " %8.1f", (double)h[(size_t)w * 8 + i] / units);
+            fprintf(stderr, "\n");
         }
     }
     return RB_OK;
