@@ -196,8 +196,10 @@ __device__ __forceinline__ float min16(const uint32_t *v)
     return fminf(r0, r1);
 }
 
-// Phase profile (RB_TC_TRACE): every warp's lane 0 of CTA 0 accumulates clock() deltas per phase in registers and
-// writes them once at the end: trace[warp * 8 + phase].  Phase meanings are per role (see the host-side dump).
+// Phase profile (build with -DRB_TC_PHASES, run with RB_TC_TRACE=1): lane 0 of every warp of CTA 0 accumulates clock()
+// deltas per phase in registers and writes them once at the end: trace[warp * 8 + phase].  Phase meanings are per
+// role (see the host-side dump).  Compiled out by default.
+#ifdef RB_TC_PHASES
 #define RB_PH_BEGIN() unsigned ph_t = clock(); unsigned long long ph_acc[6] = {0, 0, 0, 0, 0, 0}; (void)ph_t; (void)ph_acc
 #define RB_PH(i)                                   \
     do {                                           \
@@ -212,6 +214,11 @@ __device__ __forceinline__ float min16(const uint32_t *v)
         if (p.trace != nullptr && blockIdx.x == 0 && lane == 0)                                           \
             for (int i_ = 0; i_ < 6; i_++) p.trace[warp * 8 + i_] = (long long)ph_acc[i_];                \
     } while (0)
+#else
+#define RB_PH_BEGIN() do { } while (0)
+#define RB_PH(i) do { } while (0)
+#define RB_PH_END() do { } while (0)
+#endif
 
 template <int DSUB>
 __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_constant__ EncParams p,
@@ -651,7 +658,11 @@ rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const flo
     RB_TRY(make_x_tensor_map(x, n, cb.M * cb.dsub, ldx, (size_t)plan.pitch_f, &tmap));
     auto kern = encode_tc_kernel<DSUB>;
     RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+#ifdef RB_TC_PHASES
     const bool trace = getenv("RB_TC_TRACE") != nullptr;
+#else
+    const bool trace = false;
+#endif
     const size_t trace_len = (size_t)(kThreads / 32) * 8;
     if (trace) {
         RB_CUDA_TRY(cudaMalloc(&p.trace, trace_len * sizeof(long long)));
