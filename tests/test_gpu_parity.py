@@ -398,3 +398,33 @@ def test_chained_accumulate_equals_one_pass(oracle, torch_cuda):
     want = np.stack([oracle.kmeans_iteration(np.ascontiguousarray(x[:, m * dsub:(m + 1) * dsub]), init[m])[0]
                      for m in range(M)])
     assert np.array_equal(cen.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,M,k,dsub", [
+    (100_003, 30, 256, 10),   # C2 geometry: three column groups in a cluster, two lookups per 16-byte piece, ragged n*M
+    (70_001, 96, 256, 8),     # C3 geometry: eight line-aligned groups, small code tiles
+    (50_000, 16, 200, 8),     # k < 256: range-checked codes
+    (33_333, 50, 64, 6),      # dsub % 4 == 2 with several groups
+    (300, 12, 256, 4),        # one tile, fewer rows than a tile
+])
+def test_tiled_gather_bit_exact_and_range_checked(oracle, torch_cuda, n, M, k, dsub):
+    """gather_tile_kernel (TMA-staged code ring, fixed column per thread, cluster lockstep) against the oracle's
+    copy loop (primitives.rs:110-173), into a dense and into a row-padded output; a code >= k is reported."""
+    torch = torch_cuda
+    q = random_codebook(M, k, dsub, 300 + n)
+    codes = np.random.default_rng(n).integers(0, k, size=(n, M)).astype(np.uint8)
+    want = oracle.reconstruct_batch(q, None, codes, n_threads=8)
+    pq = rb.Pq(None, q)
+    cd = torch.from_numpy(codes).cuda()
+    rec = pq.reconstruct_batch(cd)
+    assert np.array_equal(rec.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    padded = torch.full((n, M * dsub + 8), -7.0, device="cuda")
+    pq.reconstruct_batch_into(cd, padded[:, :M * dsub])
+    got = padded.cpu().numpy()
+    assert np.array_equal(got[:, :M * dsub].view(np.uint32), want.view(np.uint32))
+    assert (got[:, M * dsub:] == -7.0).all()  # nothing written past the row
+    if k < 256:
+        bad = cd.clone()
+        bad[n // 2, M - 1] = k
+        with pytest.raises(IndexError):  # the reference's ndarray index panic
+            pq.reconstruct_batch(bad)
