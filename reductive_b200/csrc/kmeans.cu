@@ -252,9 +252,9 @@ ordered_sum_kernel(const float *__restrict__ x, long long ldx, long long n, int 
 //     offsets by code entirely in shared memory (histogram with shared atomics; stable placement with warp-sequential
 //     steps whose same-code groups come from 8 ballots, one per code bit), written out as one contiguous, fully
 //     coalesced u16 segment plus the k+1 cluster boundaries of the chunk;
-//   ordered_chain_kernel  launched once per chunk, one warp per (subquantizer, cluster): 32 rows per batch — 32 row
-//     gathers in flight (lanes = row slot x component), then the reference's sequential f32 adds (kmeans.rs:185-189)
-//     replayed through shuffles; the running sums live in `packed` between launches.  Because every chain is in
+//   ordered_chain_kernel  launched once per chunk; lanes = (chain, component): a warp carries 32 / dsub clusters, each
+//     lane walks its own cluster's rows in order with 8 gathers in flight and does the reference's sequential f32
+//     adds (kmeans.rs:185-189) without any cross-lane traffic; the running sums live in `packed` between launches.  Because every chain is in
 //     the same chunk at the same time, the chunk's rows (< 96 MB, inside L2) are fetched from HBM once although
 //     each (row, subquantizer) piece is gathered by a different warp.  `init` (or nullptr) continues chains started
 //     on another rank: data-parallel training can pass the running sums from rank to rank and stay bit-identical.
@@ -262,9 +262,12 @@ constexpr int kLocalThreads = 512;
 constexpr int kLocalWarps = kLocalThreads / 32;
 
 // rows per chunk: a power of two in [4096, 65536] (u16 offsets) whose x rows (4*d bytes each) stay below ~96 MB of L2
+#ifndef RB_CHUNK_MB
+#define RB_CHUNK_MB 96
+#endif
 int chunk_rows_for(size_t d)
 {
-    size_t rows = ((size_t)96 << 20) / (4 * (d ? d : 1));
+    size_t rows = ((size_t)RB_CHUNK_MB << 20) / (4 * (d ? d : 1));
     int p = 4096;
     while (p < 65536 && (size_t)(2 * p) <= rows) p *= 2;
     return p;
@@ -368,58 +371,87 @@ sort_local_kernel(const uint8_t *__restrict__ codes, long long code_pitch, long 
     for (int j = threadIdx.x; j <= k; j += kLocalThreads) ls[j] = cstart[j];
 }
 
+// read-only load that asks L2 to bring in the whole 128-byte line: the line's other three 32-byte pieces belong to
+// neighbouring subquantizers of the same row and are gathered by other warps during the same launch
+__device__ __forceinline__ float ldg_l2_128(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L2::128B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 template <int DSUB>
 __global__ void __launch_bounds__(256)
 ordered_chain_kernel(const float *__restrict__ x, long long ldx, int M, int k, int n_chunks, int chunk, int kChunkRows,
                      const uint16_t *__restrict__ list, const uint32_t *__restrict__ lstart,
                      const float *__restrict__ init, float *__restrict__ packed)
 {
-    constexpr int R = 32 / DSUB;            // row slots per gather instruction
-    constexpr int U = (32 + R - 1) / R;     // gather instructions per batch of 32 rows
+    // lanes = (chain c, component t): a warp carries 32 / DSUB independent chains, i.e. clusters; every lane walks
+    // its own cluster's rows of this chunk in order, so the reference's sequential adds need no cross-lane traffic
+    constexpr int CH = 32 / DSUB;  // chains per warp
+#ifndef RB_CHAIN_UN
+#define RB_CHAIN_UN 8
+#endif
+    constexpr int UN = RB_CHAIN_UN;  // rows in flight per chain
     const int lane = threadIdx.x & 31;
-    const long long mj = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (mj >= (long long)M * k) return;  // whole warp
-    const int m = (int)(mj / k), j = (int)(mj % k);
-    const int r = lane / DSUB, t = lane % DSUB;
-    const bool lane_on = r < R;
-    const long long chains = (long long)M * k * DSUB;
-    const float *xc = x + (long long)m * DSUB + t;
+    const int c = lane / DSUB, t = lane % DSUB;
+    const long long total_mj = (long long)M * k;
+    const long long mj = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * CH + c;
+    const bool on = c < CH && mj < total_mj;
+    const long long chains = total_mj * DSUB;
+    const long long mjc = on ? mj : 0;
+    const int m = (int)(mjc / k), j = (int)(mjc % k);
     // the chain so far: other ranks' rows (init) before this rank's first chunk, else what the last launch left
     const float *prev = chunk == 0 ? init : packed;
-    float acc = prev ? prev[mj * DSUB + t] : 0.f;
+    float acc = (on && prev) ? prev[mjc * DSUB + t] : 0.f;
     double sq = 0.0;
-    const uint32_t *ls = lstart + ((size_t)chunk * M + m) * (k + 1) + j;
-    const unsigned s = __ldg(ls), e = __ldg(ls + 1);
-    const uint16_t *seg = list + ((size_t)m * n_chunks + chunk) * kChunkRows;
-    const long long row_base = (long long)chunk * kChunkRows;
-    for (unsigned i = s; i < e; i += 32) {
-        const int cnt = (int)min(32u, e - i);
-        const unsigned off_l = lane < cnt ? (unsigned)__ldg(seg + i + lane) : 0u;
-        float v[U];
+    unsigned s = 0, e = 0;
+    if (on) {
+        const uint32_t *ls = lstart + ((size_t)chunk * M + m) * (k + 1) + j;
+        s = __ldg(ls);
+        e = __ldg(ls + 1);
+    }
+    // byte offsets in 32 bits where possible: a row offset inside the chunk is < 65 536 and the row pitch in bytes fits
+    // 32 bits, so one IMAD.WIDE.U32 per gather forms the address
+    const uint16_t *sp = list + ((size_t)m * n_chunks + chunk) * kChunkRows + s;
+    const char *xc = reinterpret_cast<const char *>(x + (long long)chunk * kChunkRows * ldx + (long long)m * DSUB + t);
+    const unsigned pitch_b = (unsigned)ldx * 4u;
+    float sqf = 0.f;  // this lane's share of sum ||x||^2 in this chunk (<= a few hundred terms), widened once below
+    int rem = (int)(e - s);
+    const uint16_t *seg0 = list + ((size_t)m * n_chunks + chunk) * kChunkRows;  // always readable
+    while (__any_sync(0xffffffffu, rem > 0)) {
+        // loads are unconditional (indices clamped to the last valid row, finished chains re-read the segment start);
+        // only the adds are predicated
+        const uint16_t *spu = rem > 0 ? sp : seg0;
+        const int last = max(min(rem, UN), 1) - 1;
+        unsigned off[UN];
+        float v[UN];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int slot = u * R + r;
-            const unsigned off = __shfl_sync(0xffffffffu, off_l, slot & 31);
-            const bool valid = lane_on && slot < cnt;
-            v[u] = valid ? __ldg(xc + (row_base + off) * ldx) : 0.f;
-            sq += (double)v[u] * (double)v[u];
-        }
-        // the reference's chain: rows in increasing order, one rounded add each
+        for (int u = 0; u < UN; u++) off[u] = (unsigned)__ldg(spu + min(u, last));
 #pragma unroll
-        for (int u = 0; u < U; u++) {
+        for (int u = 0; u < UN; u++) v[u] = ldg_l2_128(reinterpret_cast<const float *>(xc + (unsigned long long)off[u] * (unsigned long long)pitch_b));
 #pragma unroll
-            for (int rr = 0; rr < R; rr++) {
-                const int slot = u * R + rr;
-                const float vv = __shfl_sync(0xffffffffu, v[u], (rr * DSUB + t) & 31);
-                if (slot < cnt) acc = __fadd_rn(acc, vv);
+        for (int u = 0; u < UN; u++) {
+            if (u < rem) {
+                acc = __fadd_rn(acc, v[u]);  // kmeans.rs:185-189: one rounded add per row, in row order
+                sqf = fmaf(v[u], v[u], sqf);
             }
         }
+        sp += UN;
+        rem -= UN;
     }
-    if (lane < DSUB) packed[mj * DSUB + t] = acc;
-    if (lane == 0) packed[chains + mj] = (prev ? prev[chains + mj] : 0.f) + (float)(e - s);
+    sq = (double)sqf;
+    if (on) {
+        packed[mj * DSUB + t] = acc;
+        if (t == 0) packed[chains + mj] = (prev ? prev[chains + mj] : 0.f) + (float)(e - s);
+    }
+    // sum of squares: reduce over the chain's DSUB lanes (they are consecutive), one atomic per chain
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-    if (lane == 0 && sq != 0.0) atomicAdd(packed + chains + (long long)M * k + m, (float)sq);
+    for (int off2 = 1; off2 < DSUB; off2 <<= 1) {
+        const double o = __shfl_down_sync(0xffffffffu, sq, off2);
+        if (t + off2 < DSUB) sq += o;
+    }
+    if (on && t == 0 && sq != 0.0) atomicAdd(packed + chains + total_mj + m, (float)sq);
 }
 
 bool fast_ordered_supported(size_t n, size_t k, size_t dsub)
@@ -452,7 +484,7 @@ rb_status launch_ordered_fast(const float *x, size_t n, ptrdiff_t ldx, const uin
             RB_CUDA_TRY(cudaMemcpyAsync(packed + M * k * dsub + M * k, init + M * k * dsub + M * k, M * sizeof(float),
                                         cudaMemcpyDeviceToDevice, stream));
         }
-        const unsigned blocks = (unsigned)ceil_div(M * k, 8);
+        const unsigned blocks = (unsigned)ceil_div(ceil_div(M * k, 32 / dsub), 8);
         for (size_t c = 0; c < n_chunks; c++) {
 #define RB_CHAIN(D)                                                                                                  \
     case D:                                                                                                          \
@@ -587,7 +619,7 @@ rb_status launch_kmeans_accumulate(const float *x, size_t n, ptrdiff_t ldx, cons
                                    const float *init, float *packed, int ordered, cudaStream_t stream)
 {
     const size_t len = rb_kmeans_packed_len(M, k, dsub);
-    if (init && !(ordered && codes8 && fast_ordered_supported(n, k, dsub))) {
+    if (init && !(ordered && codes8 && fast_ordered_supported(n, k, dsub) && ldx > 0 && ldx < ((ptrdiff_t)1 << 29))) {
         set_error("continuing chains (init) needs the ordered update with u8 codes (k <= 256, dsub <= 32)");
         return RB_ERR_UNSUPPORTED;
     }
@@ -597,7 +629,7 @@ rb_status launch_kmeans_accumulate(const float *x, size_t n, ptrdiff_t ldx, cons
         return RB_OK;
     }
     RB_CUDA_TRY(cudaMemsetAsync(packed, 0, len * sizeof(float), stream));
-    if (ordered && codes8 && fast_ordered_supported(n, k, dsub))
+    if (ordered && codes8 && fast_ordered_supported(n, k, dsub) && ldx > 0 && ldx < ((ptrdiff_t)1 << 29))
         return launch_ordered_fast(x, n, ldx, codes8, code_pitch, M, k, dsub, init, packed, stream);
     if (ordered && k <= 1024 && n < ((size_t)1 << 32)) {
         if (codes8) return launch_ordered_t<uint8_t>(x, n, ldx, codes8, code_pitch, M, k, dsub, packed, stream);
