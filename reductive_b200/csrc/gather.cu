@@ -152,17 +152,18 @@ gather_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, cons
 // contiguous bytes.  Blocks of the column groups of one strip have adjacent block indices: they run concurrently
 // and the 32-byte sectors straddling a group boundary are completed in L2.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kTileConsumers = 512;
-constexpr int kTileThreads = kTileConsumers + 32;  // + the producer warp
 constexpr int kTileStages = 4;
 
-template <bool QUAD, bool CHECK>
-__global__ void __launch_bounds__(kTileThreads, 2)
+// CONS consumer threads + one producer warp; two blocks of 512 + 32 per SM, or one block of 992 + 32 (the 1024-thread limit) holding twice the
+// codebook (fewer, wider column groups: wider contiguous stripes and fewer re-reads of the code bytes).
+template <bool QUAD, bool CHECK, int CONS>
+__global__ void __launch_bounds__(CONS + 32, CONS == 512 ? 2 : 1)
 gather_tile_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, const uint8_t *__restrict__ codes,
                    long long n, float *__restrict__ out, long long ldo, int m_per_group, int n_groups,
                    int tile_rows, long long tiles_per_strip, int cb_floats_max, int *__restrict__ err_flag, int lockstep)
 {
     using namespace ptx;
+    constexpr int kTileConsumers = CONS, kTileThreads = CONS + 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int g = blockIdx.x % n_groups;
     const long long strip = blockIdx.x / n_groups;
@@ -291,31 +292,57 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
     if ((reinterpret_cast<uintptr_t>(out) & 15) || (ldo & 3) || (reinterpret_cast<uintptr_t>(codes) & 15)) return false;
     if ((reinterpret_cast<uintptr_t>(cb.quantizers) & 15) || n < 256) return false;
     const size_t per_m = (size_t)k * dsub * sizeof(float);
-    const size_t smem_budget = 113 * 1024;  // two blocks per SM
-    const size_t cb_budget = 100 * 1024;
     const int step = (dsub % 4 == 0) ? 1 : 2;  // group width must be a multiple of 4 floats
-    int mg = (int)(cb_budget / per_m);
-    if ((size_t)mg * dsub / 4 > (size_t)kTileConsumers) mg = kTileConsumers * 4 / dsub;  // one 16-byte piece per thread
-    mg -= mg % step;
-    if (mg < step) return false;
-    if (mg > M) mg = M;
-    int n_groups = (int)ceil_div(M, mg);
-    mg = (int)ceil_div(M, n_groups);
-    mg += (step - mg % step) % step;
-    n_groups = (int)ceil_div(M, mg);
-    if (((M - (n_groups - 1) * mg) * dsub) % 4 != 0) return false;  // last group's width
-    if ((size_t)mg * k * dsub % 4 != 0 || (size_t)mg * dsub / 4 > (size_t)kTileConsumers) return false;
-    const size_t cb_bytes = (size_t)mg * per_m;
-    const size_t bar_bytes = 2 * kTileStages * sizeof(uint64_t);
-    if (cb_bytes + bar_bytes + (size_t)kTileStages * 16 * M > smem_budget) return false;
-    int tile_rows = (int)((smem_budget - cb_bytes - bar_bytes) / kTileStages / M);
-    tile_rows -= tile_rows % 16;
-    if (tile_rows > 256) tile_rows = 256;
-    const size_t smem = cb_bytes + (size_t)kTileStages * tile_rows * M + bar_bytes;
+    struct Shape {
+        int cons = 0, mg = 0, n_groups = 0, tile_rows = 0;
+        size_t cb_bytes = 0, smem = 0;
+    };
+    // column groups for a block of `cons` consumers with `smem_budget` bytes of shared memory; n_groups == 0: no fit
+    auto shape_for = [&](int cons, size_t smem_budget, size_t cb_budget) {
+        Shape sh;
+        sh.cons = cons;
+        int mg = (int)(cb_budget / per_m);
+        if ((size_t)mg * dsub / 4 > (size_t)cons) mg = cons * 4 / dsub;  // one 16-byte piece per thread
+        mg -= mg % step;
+        if (mg < step) return sh;
+        if (mg > M) mg = M;
+        int n_groups = (int)ceil_div(M, mg);
+        mg = (int)ceil_div(M, n_groups);
+        mg += (step - mg % step) % step;
+        n_groups = (int)ceil_div(M, mg);
+        if (((M - (n_groups - 1) * mg) * dsub) % 4 != 0) return sh;  // last group's width
+        if ((size_t)mg * k * dsub % 4 != 0 || (size_t)mg * dsub / 4 > (size_t)cons) return sh;
+        const size_t cb_bytes = (size_t)mg * per_m;
+        const size_t bar_bytes = 2 * kTileStages * sizeof(uint64_t);
+        if (cb_bytes + bar_bytes + (size_t)kTileStages * 16 * M > smem_budget) return sh;
+        int tile_rows = (int)((smem_budget - cb_bytes - bar_bytes) / kTileStages / M);
+        tile_rows -= tile_rows % 16;
+        if (tile_rows > 256) tile_rows = 256;
+        sh.mg = mg;
+        sh.n_groups = n_groups;
+        sh.tile_rows = tile_rows;
+        sh.cb_bytes = cb_bytes;
+        sh.smem = cb_bytes + (size_t)kTileStages * tile_rows * M + bar_bytes;
+        return sh;
+    };
+    Shape sh = shape_for(512, 113 * 1024, 100 * 1024);   // two blocks per SM
+    const Shape big = shape_for(992, 225 * 1024, 200 * 1024);  // one block per SM
+    // the big block pays off when it removes column groups whose stripes are not whole 128-byte lines
+    {
+        const bool small_aligned = sh.n_groups > 0 && (reinterpret_cast<uintptr_t>(out) % 128 == 0) && (ldo % 32 == 0) &&
+                                   ((sh.mg * dsub) % 32 == 0);
+        if (big.n_groups > 0 && (sh.n_groups == 0 || (big.n_groups < sh.n_groups && !small_aligned))) sh = big;
+    }
+    if (sh.n_groups == 0) return false;
+    const int mg = sh.mg, n_groups = sh.n_groups, tile_rows = sh.tile_rows, blocks_per_sm = sh.cons == 512 ? 2 : 1;
+    const size_t cb_bytes = sh.cb_bytes, smem = sh.smem;
 
     const bool quad = dsub % 4 == 0, check = k < 256;
-    auto kern = quad ? (check ? gather_tile_kernel<true, true> : gather_tile_kernel<true, false>)
-                     : (check ? gather_tile_kernel<false, true> : gather_tile_kernel<false, false>);
+    auto kern = sh.cons == 512
+                    ? (quad ? (check ? gather_tile_kernel<true, true, 512> : gather_tile_kernel<true, false, 512>)
+                            : (check ? gather_tile_kernel<false, true, 512> : gather_tile_kernel<false, false, 512>))
+                    : (quad ? (check ? gather_tile_kernel<true, true, 992> : gather_tile_kernel<true, false, 992>)
+                            : (check ? gather_tile_kernel<false, true, 992> : gather_tile_kernel<false, false, 992>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -328,7 +355,7 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
     const bool lines_aligned = (reinterpret_cast<uintptr_t>(out) % 128 == 0) && (ldo % 32 == 0) && ((mg * dsub) % 32 == 0);
     const int lockstep = (n_groups > 1 && n_groups <= 8 && !lines_aligned) ? 1 : 0;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kTileThreads);
+    cfg.blockDim = dim3((unsigned)sh.cons + 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -341,7 +368,7 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
 
     // one resident wave: as many strips as clusters (or blocks) fit on the device at once
     const long long n_tiles = (long long)ceil_div(n, (size_t)tile_rows);
-    long long strips = (2 * 148) / n_groups;
+    long long strips = (blocks_per_sm * 148) / n_groups;
     if (lockstep) {
         int max_clusters = 0;
         cfg.gridDim = dim3((unsigned)(strips * n_groups));
