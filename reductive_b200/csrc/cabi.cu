@@ -88,6 +88,7 @@ struct rb_pq {
     float *q_dev = nullptr;     // [M,k,dsub]
     float *cs_dev = nullptr;    // [M,k]
     float *proj_dev = nullptr;  // [d,d] or null
+    float *projt_dev = nullptr; // its transpose: decode multiplies by R^T as a plain row-major matrix (same FMA order)
     TensorOperands tc;          // bf16-split codebook for the tcgen05 path (may be empty)
     std::vector<float> q_host, proj_host;
     DeviceCodebook cb() const { return DeviceCodebook{q_dev, cs_dev, M, k, dsub}; }
@@ -168,7 +169,7 @@ static rb_status reconstruct_batch_device(const rb_pq *pq, const void *codes, in
         RB_TRY(launch_gather(cb, csrc, code_width, rows, crs, ccs, y.as<float>(), (ptrdiff_t)d, err_flag, stream));
         if (pq->proj_dev) {  // pq.rs:323-326: reconstructions.dot(&projection.t()), then assign
             float *pdst = direct ? odst : z.as<float>();
-            RB_TRY(launch_project(y.as<float>(), rows, d, (ptrdiff_t)d, 1, pq->proj_dev, 1, pdst, stream));
+            RB_TRY(launch_project(y.as<float>(), rows, d, (ptrdiff_t)d, 1, pq->projt_dev, 0, pdst, stream));
             if (!direct) RB_TRY(launch_unpack_rows(z.as<float>(), rows, d, odst, ors, ocs, stream));
         } else {
             RB_TRY(launch_unpack_rows(y.as<float>(), rows, d, odst, ors, ocs, stream));
@@ -425,6 +426,11 @@ rb_status rb_pq_create(const float *quantizers, size_t M, size_t k, size_t dsub,
             pq->proj_host.assign(projection, projection + pq->d * pq->d);
             RB_CUDA_TRY(cudaMalloc(&pq->proj_dev, pq->d * pq->d * sizeof(float)));
             RB_CUDA_TRY(cudaMemcpy(pq->proj_dev, projection, pq->d * pq->d * sizeof(float), cudaMemcpyHostToDevice));
+            std::vector<float> rt(pq->d * pq->d);
+            for (size_t i = 0; i < pq->d; i++)
+                for (size_t j = 0; j < pq->d; j++) rt[j * pq->d + i] = projection[i * pq->d + j];
+            RB_CUDA_TRY(cudaMalloc(&pq->projt_dev, pq->d * pq->d * sizeof(float)));
+            RB_CUDA_TRY(cudaMemcpy(pq->projt_dev, rt.data(), pq->d * pq->d * sizeof(float), cudaMemcpyHostToDevice));
         }
         RB_TRY(pq->tc.prepare(pq->cb(), nullptr));
         RB_CUDA_TRY(cudaStreamSynchronize(nullptr));
@@ -446,6 +452,7 @@ void rb_pq_destroy(rb_pq *pq)
     cudaFree(pq->q_dev);
     cudaFree(pq->cs_dev);
     cudaFree(pq->proj_dev);
+    cudaFree(pq->projt_dev);
     delete pq;
 }
 

@@ -8,7 +8,7 @@
 // K), so rx is bit-identical to the oracle's and the codes that follow are bit-exact end to end.
 //
 // Bound: FP32 FMA pipe (2*d^2 flop per row).  project_fast_kernel is a register-tiled SIMT SGEMM (128 x 64 block
-// tile, 8 x 4 per thread, K steps of 16 double-buffered through shared memory, 16-byte global and shared accesses);
+// tile, 8 x 4 per thread, K steps of 16 through a 3-stage cp.async ring, 16-byte global and shared accesses);
 // project_kernel is the general-stride fallback.  A tcgen05 3xBF16 split would be several times faster still but
 // not bit-identical; it is listed as follow-up work in DESIGN.md.
 #include "common.cuh"
@@ -96,65 +96,52 @@ project_kernel(const float *__restrict__ x, long long n, int d, long long rsx, l
     }
 }
 
-// ---- fast path: unit column stride, 16-byte aligned rows, d % 4 == 0 ----------------------------------------
-constexpr int PM = 128, PN = 64, PK = 16;
-#ifndef PROJ_BLOCKS
-#define PROJ_BLOCKS 1
-#endif
+// ---- fast path: unit column stride, 16-byte aligned rows, d % 4 == 0, R not transposed ------------------------
+// 128 x 64 block tile, 16 x 16 threads, thread tile 8 rows (ty + 16 i) x 4 columns; K steps of 16 streamed through a
+// 3-stage shared-memory ring by cp.async (16 bytes each), operands read back as 128-bit vectors: A[row][k..k+3] (row
+// pitch 20 floats: the two rows a warp touches fall in different banks) and B[k][col..col+3].
+constexpr int PM = 128, PN = 64, PK = 16, PSTAGES = 3, PA_PITCH = PK + 4, PB_PITCH = PN + 4;
 
-template <bool TR>
-__global__ void __launch_bounds__(256, PROJ_BLOCKS)
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int bytes = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256)
 project_fast_kernel(const float *__restrict__ x, long long n, int d, long long ldx, const float *__restrict__ r,
                     float *__restrict__ out, long long ldo)
 {
-    __shared__ __align__(16) float As[2][PK][PM + 4];  // [k][row]
-    __shared__ __align__(16) float Bs[2][PK][PN + 4];  // [k][col]
+    __shared__ __align__(16) float As[PSTAGES][PM][PA_PITCH];
+    __shared__ __align__(16) float Bs[PSTAGES][PK][PB_PITCH];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const long long row0 = (long long)blockIdx.x * PM;
     const int col0 = blockIdx.y * PN;
+    const int n_steps = (d + PK - 1) / PK;
 
-    // global -> register staging of one K step (A: two float4 per thread, B: one)
-    float4 pa[2], pb;
-    auto fetch = [&](int t0) {
+    auto issue = [&](int step) {
+        if (step < n_steps) {
+            const int t0 = step * PK, st = step % PSTAGES;
 #pragma unroll
-        for (int l = 0; l < 2; l++) {
-            const int idx = tid + l * 256;
-            const int ar = idx >> 2, c4 = idx & 3;
-            const long long row = row0 + ar;
-            const int t = t0 + 4 * c4;
-            pa[l] = (row < n && t < d) ? __ldg(reinterpret_cast<const float4 *>(x + row * ldx + t)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (TR) {  // B[k][c] = R[col0 + c][t0 + k]: 16 bytes along k
-            const int bc = tid >> 2, k4 = tid & 3;
-            const int col = col0 + bc, t = t0 + 4 * k4;
-            pb = (col < d && t < d) ? __ldg(reinterpret_cast<const float4 *>(r + (size_t)col * d + t)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {   // B[k][c] = R[t0 + k][col0 + c]: 16 bytes along c
+            for (int l = 0; l < 2; l++) {
+                const int idx = tid + l * 256;
+                const int ar = idx >> 2, c4 = idx & 3;
+                const long long row = row0 + ar;
+                const int t = t0 + 4 * c4;
+                const bool ok = row < n && t < d;
+                cp_async16(&As[st][ar][4 * c4], ok ? x + row * ldx + t : x, ok);
+            }
             const int bk = tid >> 4, c4 = tid & 15;
             const int t = t0 + bk, col = col0 + 4 * c4;
-            pb = (t < d && col < d) ? __ldg(reinterpret_cast<const float4 *>(r + (size_t)t * d + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool ok = t < d && col < d;
+            cp_async16(&Bs[st][bk][4 * c4], ok ? r + (size_t)t * d + col : r, ok);
         }
-    };
-    auto stash = [&](int buf) {
-#pragma unroll
-        for (int l = 0; l < 2; l++) {
-            const int idx = tid + l * 256;
-            const int ar = idx >> 2, c4 = idx & 3;
-            As[buf][4 * c4 + 0][ar] = pa[l].x;
-            As[buf][4 * c4 + 1][ar] = pa[l].y;
-            As[buf][4 * c4 + 2][ar] = pa[l].z;
-            As[buf][4 * c4 + 3][ar] = pa[l].w;
-        }
-        if (TR) {
-            const int bc = tid >> 2, k4 = tid & 3;
-            Bs[buf][4 * k4 + 0][bc] = pb.x;
-            Bs[buf][4 * k4 + 1][bc] = pb.y;
-            Bs[buf][4 * k4 + 2][bc] = pb.z;
-            Bs[buf][4 * k4 + 3][bc] = pb.w;
-        } else {
-            const int bk = tid >> 4, c4 = tid & 15;
-            *reinterpret_cast<float4 *>(&Bs[buf][bk][4 * c4]) = pb;
-        }
+        cp_async_commit();  // one group per step, empty past the end, so the wait counts stay uniform
     };
 
     float acc[8][4], total[8][4];
@@ -164,32 +151,40 @@ project_fast_kernel(const float *__restrict__ x, long long n, int d, long long l
         for (int j = 0; j < 4; j++) acc[i][j] = total[i][j] = 0.f;
     bool have = false;
 
-    fetch(0);
-    stash(0);
-    __syncthreads();
-    int buf = 0;
-    for (int t0 = 0; t0 < d; t0 += PK, buf ^= 1) {
-        const bool more = t0 + PK < d;
-        if (more) fetch(t0 + PK);
-        auto step = [&](int kk) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 8]);
-            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 8 + 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bb[4] = {b.x, b.y, b.z, b.w};
+    issue(0);
+    issue(1);
+    for (int step = 0; step < n_steps; step++) {
+        issue(step + 2);
+        cp_async_wait<2>();  // this step's group has landed (two younger groups may be in flight)
+        __syncthreads();
+        const int st = step % PSTAGES, t0 = step * PK;
+        auto quad = [&](int kq, int kn) {  // kn (<= 4) consecutive k starting at 4 * kq, in order
+            float4 a[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const float4 *>(&As[st][ty + 16 * i][4 * kq]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = __fmaf_rn(a[i], bb[j], acc[i][j]);
+            for (int kk = 0; kk < 4; kk++) {
+                if (kk < kn) {
+                    const float4 b = *reinterpret_cast<const float4 *>(&Bs[st][4 * kq + kk][tx * 4]);
+                    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[i][j] = __fmaf_rn(av, bb[j], acc[i][j]);
+                    }
+                }
+            }
         };
         if (t0 + PK <= d) {
 #pragma unroll
-            for (int kk = 0; kk < PK; kk++) step(kk);
+            for (int kq = 0; kq < PK / 4; kq++) quad(kq, 4);
         } else {  // ragged last step: exactly the reference's d - t0 updates (a padded fma could turn -0 into +0)
-            for (int kk = 0; kk < d - t0; kk++) step(kk);
+            const int left = d - t0;
+            for (int kq = 0; 4 * kq < left; kq++) quad(kq, min(4, left - 4 * kq));
         }
         // matrixmultiply kc = 256: first block C = AB, later blocks C = C + AB
-        if (((t0 + PK) & 255) == 0 || !more) {
+        if (((t0 + PK) & 255) == 0 || step + 1 == n_steps) {
 #pragma unroll
             for (int i = 0; i < 8; i++)
 #pragma unroll
@@ -199,14 +194,13 @@ project_fast_kernel(const float *__restrict__ x, long long n, int d, long long l
                 }
             have = true;
         }
-        if (more) stash(buf ^ 1);
-        __syncthreads();
+        __syncthreads();  // everyone is done with this stage before it is refilled two steps later
     }
     const int col = col0 + tx * 4;
     if (col < d) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const long long row = row0 + ty * 8 + i;
+            const long long row = row0 + ty + 16 * i;
             if (row < n)
                 *reinterpret_cast<float4 *>(out + row * ldo + col) = make_float4(total[i][0], total[i][1], total[i][2], total[i][3]);
         }
@@ -243,12 +237,9 @@ rb_status launch_project(const float *x, size_t n, size_t d, ptrdiff_t rsx, ptrd
     if (n == 0 || d == 0) return RB_OK;
     const bool aligned = csx == 1 && d % 4 == 0 && rsx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(r) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    if (aligned) {
+    if (aligned && !transpose_r) {  // decode passes a pre-transposed copy of R instead of transpose_r (cabi.cu)
         dim3 fgrid((unsigned)ceil_div(n, PM), (unsigned)ceil_div(d, PN));
-        if (transpose_r)
-            project_fast_kernel<true><<<fgrid, 256, 0, stream>>>(x, (long long)n, (int)d, (long long)rsx, r, out, (long long)d);
-        else
-            project_fast_kernel<false><<<fgrid, 256, 0, stream>>>(x, (long long)n, (int)d, (long long)rsx, r, out, (long long)d);
+        project_fast_kernel<<<fgrid, 256, 0, stream>>>(x, (long long)n, (int)d, (long long)rsx, r, out, (long long)d);
         RB_LAUNCH_CHECK();
         return RB_OK;
     }
