@@ -60,7 +60,7 @@ typedef enum rb_mem_kind { RB_MEM_HOST = 0, RB_MEM_DEVICE = 1 } rb_mem_kind;
 typedef enum rb_encode_algo {
     RB_ENCODE_AUTO = 0,   /* tensor path when the shape allows it, otherwise exact SIMT */
     RB_ENCODE_EXACT = 1,  /* FP32 SIMT kernel evaluating the reference's FMA chain directly */
-    RB_ENCODE_TENSOR = 2  /* tcgen05 candidate pass + exact recheck of near-ties (k <= 256, k % 16 == 0) */
+    RB_ENCODE_TENSOR = 2  /* tcgen05 candidate pass + exact recheck of near-ties (64 < k <= 256) */
 } rb_encode_algo;
 
 /* Opaque product quantizer: reference `Pq<f32>` (src/pq/pq.rs:29-32) resident on one GPU. */

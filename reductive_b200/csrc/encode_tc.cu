@@ -50,7 +50,8 @@ namespace {
 using namespace ptx;
 
 constexpr int kTile = 128;   // rows per tile (UMMA M)
-constexpr int kCent = 256;   // centroids (UMMA N)
+constexpr int kCent = 256;   // centroid columns (UMMA N); codebooks with 64 < k < 256 are padded
+constexpr float kPadScore = 32768.f;  // score of a padding column (scaled units, exact in FP16)
 constexpr int kXStages = 2;
 constexpr int kMargRing = 8;
 constexpr int kThreads = 32 * 14;
@@ -104,8 +105,8 @@ __device__ __forceinline__ float scale_from_absmax(float amax, bool &bad)
 }
 
 template <int DSUB>
-__global__ void tc_prepare_kernel(const float *__restrict__ q, const float *__restrict__ cs, int M, __half *__restrict__ bop,
-                                  float *__restrict__ consts)
+__global__ void tc_prepare_kernel(const float *__restrict__ q, const float *__restrict__ cs, int M, int k,
+                                  __half *__restrict__ bop, float *__restrict__ consts)
 {
     constexpr int KPAD = kpad_of(DSUB), NCH = KPAD / 8;
     bool bad;
@@ -119,10 +120,15 @@ __global__ void tc_prepare_kernel(const float *__restrict__ q, const float *__re
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (m, j)
     if (idx >= M * kCent) return;
     const int m = idx / kCent, j = idx % kCent;
-    const float *c = q + (size_t)idx * DSUB;
     __half kv[KPAD];
 #pragma unroll
     for (int t = 0; t < KPAD; t++) kv[t] = __float2half_rn(0.f);
+    if (j >= k) {
+        // k < 256: the unused columns get a zero centroid with the constant score kPadScore, far above any real
+        // score of a row the tensor pass is allowed to decide (rows with large norms are decided exactly)
+        kv[3 * DSUB] = __float2half_rn(kPadScore);
+    } else {
+    const float *c = q + ((size_t)m * k + j) * DSUB;
 #pragma unroll
     for (int t = 0; t < DSUB; t++) {
         const float cv = c[t] * scale;
@@ -134,10 +140,11 @@ __global__ void tc_prepare_kernel(const float *__restrict__ q, const float *__re
         kv[DSUB + t] = l2;
         kv[2 * DSUB + t] = h2;
     }
-    const float csv = cs[idx] * scale2;
+    const float csv = cs[(size_t)m * k + j] * scale2;
     const __half ch = __float2half_rn(csv);
     kv[3 * DSUB] = ch;
     kv[3 * DSUB + 1] = __float2half_rn(csv - __half2float(ch));
+    }
     // [m][chunk][j][8 halves]
     __half *dst = bop + (size_t)m * NCH * kCent * 8;
 #pragma unroll
@@ -167,6 +174,7 @@ struct EncParams {
     uint32_t *n_pairs;
     uint32_t max_pairs;
     int M, gm, n_groups, a_stages, pitch_f;
+    float xs_limit;  // rows with ||x * scale||^2 at or above this are decided exactly
     long long n_tiles;
     long long *trace;  // debugging aid (RB_TC_TRACE): per-role clock64 stamps of CTA 0, else nullptr
     unsigned short cta_start[kMaxGroups + 1];  // CTAs [cta_start[g], cta_start[g+1]) own column group g
@@ -391,9 +399,10 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     }
                     w[3 * DSUB / 2] = 0x3c003c00u;  // (1.0, 1.0)
                     // NaN in x makes xs NaN, Inf makes it Inf; |x * scale| <= sqrt(xs) * scale must stay inside the
-                    // FP16 range (2^15): decide such rows exactly
+                    // FP16 range (2^15) and, for padded codebooks, real scores must stay far below kPadScore
+                    // (cs + 2 |x||c| <= 64 + 2 * 8 * sqrt(xs_sc) < 16 384 for xs_sc < 10^6): decide other rows exactly
                     const float xs_sc = xs * scale2;
-                    const bool bad = cb_bad || !(xs_sc < 1.0e9f);
+                    const bool bad = cb_bad || !(xs_sc < p.xs_limit);
                     const float csmax = p.consts[g * p.gm + ml0 + h];
                     float marg = margin_of(xs, csmax, DSUB) * scale2;
                     if (bad || !(marg < 3.0e38f)) marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
@@ -652,6 +661,7 @@ rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const flo
     p.a_stages = plan.a_stages;
     p.pitch_f = plan.pitch_f;
     p.n_tiles = (long long)n_tiles;
+    p.xs_limit = cb.k < (size_t)kCent ? 1.0e6f : 1.0e9f;
     p.trace = nullptr;
     for (int g = 0; g <= kMaxGroups; g++) p.cta_start[g] = plan.cta_start[g < plan.n_groups ? g : plan.n_groups];
     CUtensorMap tmap;
@@ -707,7 +717,8 @@ bool dsub_instantiated(size_t dsub)
 
 bool tensor_path_supported(const DeviceCodebook &cb)
 {
-    if (cb.k != (size_t)kCent || !dsub_instantiated(cb.dsub)) return false;
+    // k < 256 runs padded to 256 columns; below ~64 centroids the exact kernel (cost proportional to k) is faster
+    if (cb.k > (size_t)kCent || cb.k <= 64 || !dsub_instantiated(cb.dsub)) return false;
     return make_plan(cb.M, cb.dsub, 1u << 20, kMaxGroups).gm > 0;
 }
 
@@ -738,7 +749,7 @@ rb_status TensorOperands::prepare(const DeviceCodebook &cb, cudaStream_t stream)
     switch (cb.dsub) {
 #define X(D)                                                                                                         \
     case D:                                                                                                          \
-        tc_prepare_kernel<D><<<blocks, 128, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.M,                            \
+        tc_prepare_kernel<D><<<blocks, 128, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.M, (int)cb.k,                 \
                                                          reinterpret_cast<__half *>(b_tiles), consts);               \
         break;
         RB_TC_DSUBS(X)

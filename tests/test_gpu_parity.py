@@ -98,6 +98,8 @@ SHAPES = [  # (n, M, k, dsub)
     (8_192, 96, 256, 8),     # C3 geometry
     (16_384, 16, 256, 8),    # C5 geometry
     (100, 16, 16, 8),        # benches/pq.rs shape
+    (6_000, 6, 128, 10),     # 7-bit codebook: tensor path with padded columns
+    (5_000, 4, 200, 8),      # k not a power of two, padded
     (3_001, 4, 64, 7),       # odd dsub, ragged row count
     (1_234, 3, 100, 11),     # dsub outside the templated set -> generic kernel; k not a multiple of 16
     (777, 5, 300, 4),        # k > 256
@@ -428,3 +430,17 @@ def test_tiled_gather_bit_exact_and_range_checked(oracle, torch_cuda, n, M, k, d
         bad[n // 2, M - 1] = k
         with pytest.raises(IndexError):  # the reference's ndarray index panic
             pq.reconstruct_batch(bad)
+
+
+def test_padded_codebook_large_norm_rows_and_ties(oracle, algo):
+    """64 < k < 256 runs the tensor kernel with padding columns of a fixed large score: rows whose norm could bring a
+    real score near it must be decided exactly, near ties as usual."""
+    M, k, dsub = 4, 128, 10
+    q = random_codebook(M, k, dsub, 77)
+    x = np.concatenate([near_tie_rows(q, 4_000, 78), normal((2_000, M * dsub), 79),
+                        normal((64, M * dsub), 80) * F(1e3), normal((64, M * dsub), 81) * F(1e5),
+                        normal((64, M * dsub), 82) * F(1e-6)])
+    codes = rb.Pq(None, q).quantize_batch(x, np.uint8)
+    want = oracle.quantize_batch(q, None, x, np.uint8, n_threads=8)
+    assert codes.max() < k
+    assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ"
