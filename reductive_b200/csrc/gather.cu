@@ -386,6 +386,14 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
     e = cudaLaunchKernelEx(&cfg, kern, cb.quantizers, k, dsub, M, reinterpret_cast<const uint8_t *>(codes),
                            (long long)n, out, (long long)ldo, mg, n_groups, tile_rows, tiles_per_strip,
                            (int)(cb_bytes / sizeof(float)), err_flag, lockstep);
+    if (e != cudaSuccess && lockstep) {
+        // the cluster shape could not be placed (partitioned GPU, ...): same kernel without the lockstep barrier
+        (void)cudaGetLastError();
+        attr[0].val.clusterDim.x = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, cb.quantizers, k, dsub, M, reinterpret_cast<const uint8_t *>(codes),
+                               (long long)n, out, (long long)ldo, mg, n_groups, tile_rows, tiles_per_strip,
+                               (int)(cb_bytes / sizeof(float)), err_flag, 0);
+    }
     if (e != cudaSuccess) {
         set_error("cudaLaunchKernelEx failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);
         *status = RB_ERR_CUDA;
