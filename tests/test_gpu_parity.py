@@ -444,3 +444,21 @@ def test_padded_codebook_large_norm_rows_and_ties(oracle, algo):
     want = oracle.quantize_batch(q, None, x, np.uint8, n_threads=8)
     assert codes.max() < k
     assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ"
+
+
+@pytest.mark.parametrize("dsub", [4, 8, 10, 12, 16, 20, 30])
+@pytest.mark.parametrize("scale", [1e-4, 1.0, 3e3])
+def test_tensor_margin_holds_across_scales_and_widths(oracle, dsub, scale):
+    """The tensor pass may only decide what the reference decides the same way: near-tie rows (bisector +- ulps),
+    random rows and rows far outside the codebook, at three magnitudes and every instantiated subvector width,
+    with a codebook whose subquantizers differ in scale by 64x."""
+    M, k = 4, 256
+    q = random_codebook(M, k, dsub, 1000 + dsub)
+    q *= np.array([1.0, 8.0, 0.125, 1.0], F)[:, None, None]
+    q = (q * F(scale)).astype(F)
+    x = np.concatenate([near_tie_rows(q, 6_000, 2000 + dsub), normal((3_000, M * dsub), 3000 + dsub) * F(scale),
+                        normal((500, M * dsub), 4000 + dsub) * F(30.0 * scale)]).astype(F)
+    rb.set_encode_algo(rb.ENCODE_AUTO)
+    codes = rb.Pq(None, q).quantize_batch(x, np.uint8)
+    want = oracle.quantize_batch(q, None, x, np.uint8, n_threads=8)
+    assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ"
