@@ -277,6 +277,49 @@ def run_ours(args) -> None:
                                       "parity": "bit-identical to the one-GPU run and the oracle"}
     del x3
 
+    # C5: one 12.5M x 128 shard per GPU (100M rows over 8 GPUs), M = 16; device-generated, no collective
+    n5, M5, dsub5 = 12_500_000, 16, 8
+    pq5 = rb.Pq(None, np.random.default_rng(5).normal(size=(M5, K_CENTROIDS, dsub5)).astype(np.float32))
+    g5 = torch.Generator(device=dev)
+    g5.manual_seed(500 + rank)
+    x5 = torch.randn((n5, M5 * dsub5), generator=g5, device=dev, dtype=torch.float32)
+    c5 = torch.empty((n5, M5), dtype=torch.uint8, device=dev)
+    pq5.quantize_batch_into(x5, c5)
+    barrier()
+    k0.record(stream)
+    for _ in range(3):
+        pq5.quantize_batch_into(x5, c5)
+    k1.record(stream)
+    barrier()
+    t5 = torch.tensor([k0.elapsed_time(k1) / 3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+    extra["c5_streaming_shard"] = {"workload": f"C5: quantize_batch 12.5M x 128 per GPU x {world} GPU(s), 16 x 256 centroids",
+                                   "ms": float(t5.item()), "vectors_per_s": world * n5 / (float(t5.item()) * 1e-3)}
+    del x5, c5
+    # C4: projected (Opq / GaussianOpq) encode + decode, 1M x 300, M = 30; exact-order FP32 rotation + encode / gather
+    n4 = 1_000_000
+    r4 = np.linalg.qr(np.random.default_rng(4).normal(size=(D, D)))[0].astype(np.float32)
+    pq4 = rb.Pq(np.ascontiguousarray(r4), q)
+    x4 = x[:n4]
+    c4 = torch.empty((n4, M), dtype=torch.uint8, device=dev)
+    rec4 = torch.empty((n4, D), dtype=torch.float32, device=dev)
+    pq4.quantize_batch_into(x4, c4)
+    pq4.reconstruct_batch_into(c4, rec4)
+    barrier()
+    k0.record(stream)
+    pq4.quantize_batch_into(x4, c4)
+    k1.record(stream)
+    barrier()
+    e4 = k0.elapsed_time(k1)
+    k0.record(stream)
+    pq4.reconstruct_batch_into(c4, rec4)
+    k1.record(stream)
+    barrier()
+    extra["c4_projected"] = {"workload": "C4: 1M x 300 with a 300 x 300 projection, M = 30 (per GPU)",
+                             "encode_ms": e4, "decode_ms": k0.elapsed_time(k1)}
+    del rec4, c4
+
     if rank == 0:
         # roofline of the dominant kernel (the encode kernel is the whole step): algorithmic bytes per vector
         # = 4*d + M, against the measured HBM copy bandwidth — at the measured peaks the HBM bound
