@@ -97,10 +97,14 @@ project_kernel(const float *__restrict__ x, long long n, int d, long long rsx, l
 }
 
 // ---- fast path: unit column stride, 16-byte aligned rows, d % 4 == 0, R not transposed ------------------------
-// 128 x 64 block tile, 16 x 16 threads, thread tile 8 rows (ty + 16 i) x 4 columns; K steps of 16 streamed through a
+// 64 x 64 block tile (PROJ_PM), 16 x 16 threads, thread tile 4 rows (ty + 16 i) x 4 columns; K steps of 16 streamed through a
 // 3-stage shared-memory ring by cp.async (16 bytes each), operands read back as 128-bit vectors: A[row][k..k+3] (row
 // pitch 20 floats: the two rows a warp touches fall in different banks) and B[k][col..col+3].
-constexpr int PM = 128, PN = 64, PK = 16, PSTAGES = 3, PA_PITCH = PK + 4, PB_PITCH = PN + 4;
+#ifndef PROJ_PM
+#define PROJ_PM 64
+#endif
+constexpr int PM = PROJ_PM, PN = 64, PK = 16, PSTAGES = 3, PA_PITCH = PK + 4, PB_PITCH = PN + 4;
+constexpr int PR = PM / 16;  // rows per thread
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, bool valid)
 {
@@ -128,7 +132,7 @@ project_fast_kernel(const float *__restrict__ x, long long n, int d, long long l
         if (step < n_steps) {
             const int t0 = step * PK, st = step % PSTAGES;
 #pragma unroll
-            for (int l = 0; l < 2; l++) {
+            for (int l = 0; l < PM / 64; l++) {
                 const int idx = tid + l * 256;
                 const int ar = idx >> 2, c4 = idx & 3;
                 const long long row = row0 + ar;
@@ -144,9 +148,9 @@ project_fast_kernel(const float *__restrict__ x, long long n, int d, long long l
         cp_async_commit();  // one group per step, empty past the end, so the wait counts stay uniform
     };
 
-    float acc[8][4], total[8][4];
+    float acc[PR][4], total[PR][4];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < PR; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = total[i][j] = 0.f;
     bool have = false;
@@ -159,16 +163,16 @@ project_fast_kernel(const float *__restrict__ x, long long n, int d, long long l
         __syncthreads();
         const int st = step % PSTAGES, t0 = step * PK;
         auto quad = [&](int kq, int kn) {  // kn (<= 4) consecutive k starting at 4 * kq, in order
-            float4 a[8];
+            float4 a[PR];
 #pragma unroll
-            for (int i = 0; i < 8; i++) a[i] = *reinterpret_cast<const float4 *>(&As[st][ty + 16 * i][4 * kq]);
+            for (int i = 0; i < PR; i++) a[i] = *reinterpret_cast<const float4 *>(&As[st][ty + 16 * i][4 * kq]);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
                 if (kk < kn) {
                     const float4 b = *reinterpret_cast<const float4 *>(&Bs[st][4 * kq + kk][tx * 4]);
                     const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
+                    for (int i = 0; i < PR; i++) {
                         const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
 #pragma unroll
                         for (int j = 0; j < 4; j++) acc[i][j] = __fmaf_rn(av, bb[j], acc[i][j]);
@@ -186,7 +190,7 @@ project_fast_kernel(const float *__restrict__ x, long long n, int d, long long l
         // matrixmultiply kc = 256: first block C = AB, later blocks C = C + AB
         if (((t0 + PK) & 255) == 0 || step + 1 == n_steps) {
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < PR; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     total[i][j] = have ? __fadd_rn(total[i][j], acc[i][j]) : acc[i][j];
@@ -199,7 +203,7 @@ project_fast_kernel(const float *__restrict__ x, long long n, int d, long long l
     const int col = col0 + tx * 4;
     if (col < d) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < PR; i++) {
             const long long row = row0 + ty + 16 * i;
             if (row < n)
                 *reinterpret_cast<float4 *>(out + row * ldo + col) = make_float4(total[i][0], total[i][1], total[i][2], total[i][3]);
