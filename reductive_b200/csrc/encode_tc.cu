@@ -700,7 +700,7 @@ rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const flo
     return RB_OK;
 }
 
-#define RB_TC_DSUBS(X) X(4) X(8) X(10) X(12) X(16) X(20) X(30)
+#define RB_TC_DSUBS(X) X(2) X(4) X(6) X(8) X(10) X(12) X(16) X(20) X(24) X(30) X(32)
 
 bool dsub_instantiated(size_t dsub)
 {

@@ -446,7 +446,7 @@ def test_padded_codebook_large_norm_rows_and_ties(oracle, algo):
     assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ"
 
 
-@pytest.mark.parametrize("dsub", [4, 8, 10, 12, 16, 20, 30])
+@pytest.mark.parametrize("dsub", [2, 4, 6, 8, 10, 12, 16, 20, 24, 30, 32])
 @pytest.mark.parametrize("scale", [1e-4, 1.0, 3e3])
 def test_tensor_margin_holds_across_scales_and_widths(oracle, dsub, scale):
     """The tensor pass may only decide what the reference decides the same way: near-tie rows (bisector +- ulps),
