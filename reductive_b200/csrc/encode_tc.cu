@@ -715,6 +715,28 @@ bool dsub_instantiated(size_t dsub)
 
 }  // namespace
 
+}  // namespace rb
+
+// Host-only view of the work plan of the tensor encode kernel, for the CPU tests of its invariants (every column
+// group owns at least one CTA, CTA ranges partition [0, ctas), shared memory fits, TMA box constraints).
+// out = {gm, n_groups, a_stages, pitch_f, ctas, smem_bytes}; cta_start receives n_groups + 1 entries.  Returns 0 when
+// the shape has no plan (the exact kernel is used then).
+extern "C" int rb_debug_tensor_plan(size_t M, size_t dsub, size_t n_tiles, int sms, long long *out, unsigned short *cta_start)
+{
+    const rb::Plan p = rb::make_plan(M, dsub, n_tiles, sms > rb::kMaxGroups ? rb::kMaxGroups : sms);
+    if (p.gm == 0) return 0;
+    out[0] = p.gm;
+    out[1] = p.n_groups;
+    out[2] = p.a_stages;
+    out[3] = p.pitch_f;
+    out[4] = p.ctas;
+    out[5] = (long long)p.smem;
+    for (int g = 0; g <= p.n_groups; g++) cta_start[g] = p.cta_start[g];
+    return 1;
+}
+
+namespace rb {
+
 bool tensor_path_supported(const DeviceCodebook &cb)
 {
     // k < 256 runs padded to 256 columns; below ~64 centroids the exact kernel (cost proportional to k) is faster
