@@ -56,13 +56,18 @@ def cuda_assign(x_local, centroids):
     return codes
 
 
-def cuda_accumulate(x_local, centroids, codes, packed_before, packed) -> None:
-    """update_centroids' scatter-add of this rank's rows, continuing the chains of the preceding ranks
-    (src/kmeans.rs:181-189)."""
+def cuda_accumulate(x_local, centroids, codes, packed_before, packed, m0: int = 0, m1: Optional[int] = None) -> None:
+    """update_centroids' scatter-add of this rank's rows for the subquantizers [m0, m1), continuing the chains of the
+    preceding ranks (src/kmeans.rs:181-189).  `packed_before` / `packed` hold that slice only:
+    sums [(m1-m0),k,dsub] | counts [(m1-m0),k] | sum of squared norms [(m1-m0)]."""
     import torch
 
     M, k, dsub = centroids.shape
-    check(lib.rb_kmeans_accumulate(x_local.data_ptr(), x_local.shape[0], x_local.stride(0), codes.data_ptr(), M, k, dsub,
+    m1 = M if m1 is None else m1
+    n = x_local.shape[0]
+    pitch, width = int(lib.rb_kmeans_code_pitch(n)), int(lib.rb_kmeans_code_width(k))
+    check(lib.rb_kmeans_accumulate(x_local.data_ptr() + 4 * m0 * dsub, n, x_local.stride(0),
+                                   codes.data_ptr() + m0 * pitch * width, m1 - m0, k, dsub,
                                    None if packed_before is None else packed_before.data_ptr(), packed.data_ptr(),
                                    torch.cuda.current_stream().cuda_stream))
 
@@ -76,10 +81,15 @@ def cuda_finalize(packed, n_total: int, centroids, loss) -> None:
                                  None if loss is None else loss.data_ptr(), torch.cuda.current_stream().cuda_stream))
 
 
+def slice_len(m0: int, m1: int, k: int, dsub: int) -> int:
+    return (m1 - m0) * (k * dsub + k + 1)
+
+
 def kmeans_data_parallel(x_local, n_total: int, centroids, n_iterations: int, group=None,
                          local_step: Optional[Callable] = None, finalize: Optional[Callable] = None,
                          on_iteration: Optional[Callable] = None, mode: str = "allreduce",
-                         assign: Optional[Callable] = None, accumulate: Optional[Callable] = None):
+                         assign: Optional[Callable] = None, accumulate: Optional[Callable] = None,
+                         n_slices: Optional[int] = None):
     """Run `n_iterations` data-parallel Lloyd iterations IN PLACE on `centroids` ([M,k,dsub], identical on every
     rank); returns the per-subquantizer loss of the last iteration ([M] tensor).
 
@@ -93,8 +103,10 @@ def kmeans_data_parallel(x_local, n_total: int, centroids, n_iterations: int, gr
       at n = 1M, although the loss agrees to ~1e-6.
     mode "chained": every rank assigns its rows in parallel, then the running sums travel rank 0 -> 1 -> ... ->
       last (point-to-point) with each rank CONTINUING the chains over its rows, and the last rank broadcasts the
-      totals.  The update is serialised across ranks but the result is bit-identical to one sequential pass —
-      the oracle's and the reference's — for any number of GPUs."""
+      totals.  The result is bit-identical to one sequential pass — the oracle's and the reference's — for any
+      number of GPUs.  The subquantizers are independent, so they travel in `n_slices` slices (default:
+      min(world, 4); per-slice launches have a fixed cost) as a wavefront: while rank r continues slice s, rank r-1 already works on slice s+1, and the relay costs
+      about (world + n_slices - 1) / n_slices local updates instead of `world`."""
     import torch
     import torch.distributed as dist
 
@@ -106,27 +118,36 @@ def kmeans_data_parallel(x_local, n_total: int, centroids, n_iterations: int, gr
         raise ValueError(f"unknown mode {mode!r}")
     M, k, dsub = centroids.shape
     plen = M * k * dsub + M * k + M
-    packed = torch.empty((plen,), dtype=torch.float32, device=centroids.device)
     loss = torch.zeros((M,), dtype=torch.float32, device=centroids.device)
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     if distributed and mode == "chained":
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
-        before = torch.empty((plen,), dtype=torch.float32, device=centroids.device) if rank > 0 else None
+        ns = max(1, min(M, n_slices if n_slices is not None else min(world, 4)))
+        bounds = [(M * i) // ns for i in range(ns + 1)]
+        slices = [(bounds[i], bounds[i + 1]) for i in range(ns) if bounds[i + 1] > bounds[i]]
+        new = lambda a, b: torch.empty((slice_len(a, b, k, dsub),), dtype=torch.float32, device=centroids.device)  # noqa: E731
+        packed_s = [new(a, b) for a, b in slices]
+        before_s = [new(a, b) for a, b in slices] if rank > 0 else [None] * len(slices)
+    else:
+        packed = torch.empty((plen,), dtype=torch.float32, device=centroids.device)
     for it in range(n_iterations):
         if distributed and mode == "chained":
             codes = assign(x_local, centroids)                       # all ranks at once
-            if rank > 0:
-                dist.recv(before, src=ranks[rank - 1], group=group)  # sums over the rows of ranks < rank
-            accumulate(x_local, centroids, codes, before, packed)
-            if rank + 1 < world:
-                dist.send(packed, dst=ranks[rank + 1], group=group)
-            dist.broadcast(packed, src=ranks[world - 1], group=group)
+            for (a, b), before, mine in zip(slices, before_s, packed_s):
+                if rank > 0:
+                    dist.recv(before, src=ranks[rank - 1], group=group)  # sums over the rows of ranks < rank
+                accumulate(x_local, centroids, codes, before, mine, a, b)
+                if rank + 1 < world:
+                    dist.send(mine, dst=ranks[rank + 1], group=group)
+            for (a, b), mine in zip(slices, packed_s):
+                dist.broadcast(mine, src=ranks[world - 1], group=group)
+                finalize(mine, n_total, centroids[a:b], loss[a:b])
         else:
             local_step(x_local, centroids, packed)
             if distributed:
                 dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)  # the one exchange per iteration
-        finalize(packed, n_total, centroids, loss)
+            finalize(packed, n_total, centroids, loss)
         if on_iteration is not None:
             on_iteration(it)
     return loss

@@ -97,19 +97,22 @@ def _np_assign(o):
     return assign
 
 
-def _np_accumulate(x_local, centroids, codes, before, packed):
-    """kmeans.rs:185-189 restated: one rounded f32 add per row, in row order, continuing from `before`."""
+def _np_accumulate(x_local, centroids, codes, before, packed, m0=0, m1=None):
+    """kmeans.rs:185-189 restated: one rounded f32 add per row, in row order, continuing from `before`, for the
+    subquantizers [m0, m1) (packed layouts hold that slice only)."""
     M, k, dsub = centroids.shape
+    m1 = M if m1 is None else m1
+    ms = m1 - m0
     x = x_local.numpy()
-    n0 = M * k * dsub
-    flat = np.zeros((n0 + M * k + M,), np.float32) if before is None else before.numpy().copy()
-    sums, counts, sq = flat[:n0].reshape(M, k, dsub), flat[n0:n0 + M * k].reshape(M, k), flat[n0 + M * k:]
-    for m in range(M):
+    n0 = ms * k * dsub
+    flat = np.zeros((n0 + ms * k + ms,), np.float32) if before is None else before.numpy().copy()
+    sums, counts, sq = flat[:n0].reshape(ms, k, dsub), flat[n0:n0 + ms * k].reshape(ms, k), flat[n0 + ms * k:]
+    for m in range(m0, m1):
         sub = x[:, m * dsub:(m + 1) * dsub]
         for i, a in enumerate(codes[m]):
-            sums[m, a] = sums[m, a] + sub[i]  # float32 + float32, rounded once
-            counts[m, a] += np.float32(1)
-        sq[m] = np.float32(np.float64(sq[m]) + (sub.astype(np.float64) ** 2).sum())
+            sums[m - m0, a] = sums[m - m0, a] + sub[i]  # float32 + float32, rounded once
+            counts[m - m0, a] += np.float32(1)
+        sq[m - m0] = np.float32(np.float64(sq[m - m0]) + (sub.astype(np.float64) ** 2).sum())
     packed.copy_(torch.from_numpy(flat))
 
 
@@ -145,7 +148,7 @@ def _chained_worker(rank, world, port, n, M, k, dsub, iters, q):
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_chained_data_parallel_kmeans_is_bit_identical_to_one_process(oracle, world):
-    n, M, k, dsub, iters = 500, 2, 8, 4, 5
+    n, M, k, dsub, iters = 500, 5, 8, 4, 5
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]

@@ -394,6 +394,16 @@ def test_chained_accumulate_equals_one_pass(oracle, torch_cuda):
         cuda_accumulate(b, cen, cuda_assign(b, cen), p0, p1)
         assert torch.equal(p1[:n0].view(torch.int32), one[:n0].view(torch.int32)), cut
         assert torch.allclose(p1[n0:], one[n0:], rtol=1e-5)
+    # a slice of the subquantizers [1, 4) accumulated on its own (what the chained multi-GPU mode relays) equals the
+    # same slice of the full pass
+    from reductive_b200.dist import slice_len
+    m0, m1 = 1, 4
+    ps = torch.empty((slice_len(m0, m1, k, dsub),), dtype=torch.float32, device="cuda")
+    codes_all = cuda_assign(xd, cen)
+    cuda_accumulate(xd, cen, codes_all, None, ps, m0, m1)
+    ns = (m1 - m0) * k * dsub
+    assert torch.equal(ps[:ns].view(torch.int32), one[m0 * k * dsub:m1 * k * dsub].view(torch.int32))
+    assert torch.equal(ps[ns:ns + (m1 - m0) * k], one[M * k * dsub + m0 * k:M * k * dsub + m1 * k])
     # and the finalized centroids are the oracle's
     loss = torch.zeros((M,), device="cuda")
     cuda_finalize(one, n, cen, loss)
