@@ -109,7 +109,9 @@ rb_status rb_pq_quantize_vector(const rb_pq *pq, const float *x, ptrdiff_t x_str
 /* ---- Reconstruct (src/pq/traits.rs:102-156; impl pq.rs:305-348) ------------------------------- */
 
 /* reconstruct_batch_into  pq.rs:309-327 -> primitives.rs:150-173 (+ out = out . R^T).  RB_ERR_CODE_RANGE
- * if any code >= k (detected on the device; output rows with a bad code are unspecified). */
+ * if any code >= k (detected on the device; output rows with a bad code are unspecified).  Reporting that
+ * status needs the kernel's result, so a device-memory call synchronises `stream` -- except when no code value can
+ * be out of range (code_width 1, k = 256), where it stays asynchronous. */
 rb_status rb_pq_reconstruct_batch(const rb_pq *pq, const void *codes, int code_width, size_t n,
                                   ptrdiff_t code_row_stride, ptrdiff_t code_col_stride, float *out,
                                   ptrdiff_t out_row_stride, ptrdiff_t out_col_stride, int mem_kind,

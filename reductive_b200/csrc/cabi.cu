@@ -548,7 +548,10 @@ rb_status rb_pq_reconstruct_batch(const rb_pq *pq, const void *codes, int code_w
     RB_TRY(flag.alloc(sizeof(int), st));
     RB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
     RB_TRY(reconstruct_batch_device(pq, codes, code_width, n, crs, ccs, out, ors, ocs, flag.as<int>(), st));
-    int bad = 0;  // reporting an out-of-range code needs the result: this call synchronises `stream`
+    // reporting an out-of-range code needs the result, so the call synchronises `stream` -- unless no code value
+    // can be out of range (u8 codes of a 256-centroid quantizer), in which case it stays asynchronous
+    if (code_width == 1 && pq->k >= 256) return RB_OK;
+    int bad = 0;
     RB_CUDA_TRY(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     RB_CUDA_TRY(cudaStreamSynchronize(st));
     if (bad) return fail(RB_ERR_CODE_RANGE, "a code is >= the number of centroids (%zu)", pq->k);

@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
+#include <cstdlib>
+
 namespace rb {
 
 namespace {
@@ -139,91 +141,105 @@ gather_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fast path (u8 codes, dense [n, M] code matrix, 16-byte aligned output rows, even dsub): tiled gather.
+// Fast path (u8 codes, dense [n, M] code matrix, 16-byte aligned output rows, even dsub, d % 4 == 0): tiled gather.
 //
-// A block owns one column group (a whole number of subquantizers whose width in floats is a multiple of 4; its
-// codebook slice lives in shared memory for the block's lifetime) and walks a strip of row tiles.  The code bytes
-// of a tile's rows are contiguous in global memory; a producer thread streams them through a ring of shared-memory
-// stages with cp.async.bulk (TMA engine) + mbarriers, several tiles ahead, so the consumer warps never wait on a
-// global load and never hit a block-wide barrier in the steady state.  A consumer thread keeps a fixed 16-byte
-// column position (so its centroid offsets are loop-invariant registers) and walks the rows of the tile: per
-// piece it reads one or two code bytes and one 16-byte / two 8-byte centroid pieces from shared memory and issues
-// one 16-byte store.  Consecutive lanes own consecutive pieces of a row -> a warp store writes 512
-// contiguous bytes.  Blocks of the column groups of one strip have adjacent block indices: they run concurrently
-// and the 32-byte sectors straddling a group boundary are completed in L2.
+// A block owns one column group — `gw` consecutive output columns, not necessarily whole subquantizers — and walks
+// a strip of row tiles.  Its slice of the codebook lives in shared memory for the block's lifetime in a
+// COLUMN-ALIGNED layout: cbt[c][j] = value of output column col_lo + j when that column's subquantizer has code c,
+// row pitch W a multiple of 32 floats.  The bank of cbt[c][j] is then j mod 32 whatever c is, so the eight lanes
+// of a quarter warp, which own consecutive 16-byte pieces of one row, read 32 distinct banks: the scattered
+// centroid reads are conflict free by construction (the natural [m][c][dsub] layout replayed 58 % of them).
+// The code bytes of a tile's rows are contiguous in global memory; a producer thread streams them through a ring of
+// shared-memory stages with cp.async.bulk (TMA engine) + mbarriers, several tiles ahead, so the consumer warps
+// never wait on a global load and never hit a block-wide barrier in the steady state.  A consumer thread keeps a
+// fixed 16-byte column position: per row it reads one code byte and one 16-byte piece (a piece that straddles two
+// subquantizers takes its upper half with a second code byte and an 8-byte read) and issues one 16-byte store.
+// Consecutive lanes own consecutive pieces of a row -> a warp store writes 512 contiguous bytes.  Blocks of the
+// column groups of one strip have adjacent block indices: they run concurrently (as a cluster in lockstep when
+// the stripes are not whole lines) and the sectors straddling a group boundary are completed in L2.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kTileStages = 4;
+constexpr int kMaxTileStages = 8;
+#ifndef RB_GATHER_UNROLL
+#define RB_GATHER_UNROLL 4
+#endif
+constexpr int kGatherUnroll = RB_GATHER_UNROLL;
 
-// CONS consumer threads + one producer warp; two blocks of 512 + 32 per SM, or one block of 992 + 32 (the 1024-thread limit) holding twice the
-// codebook (fewer, wider column groups: wider contiguous stripes and fewer re-reads of the code bytes).
-template <bool QUAD, bool CHECK, int CONS>
+// CONS consumer threads + one producer warp; two blocks of 512 + 32 per SM, or one block of 992 + 32 (the
+// 1024-thread limit) holding twice the columns (fewer, wider column groups).
+template <bool CHECK, int CONS>
 __global__ void __launch_bounds__(CONS + 32, CONS == 512 ? 2 : 1)
 gather_tile_kernel(const float *__restrict__ quantizers, int k, int dsub, int M, const uint8_t *__restrict__ codes,
-                   long long n, float *__restrict__ out, long long ldo, int m_per_group, int n_groups,
-                   int tile_rows, long long tiles_per_strip, int cb_floats_max, int *__restrict__ err_flag, int lockstep)
+                   long long n, float *__restrict__ out, long long ldo, int gw, int n_groups, int W, int tile_rows,
+                   int stages, long long tiles_per_strip, long long tile_step, int *__restrict__ err_flag, int lockstep)
 {
     using namespace ptx;
     constexpr int kTileConsumers = CONS, kTileThreads = CONS + 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int g = blockIdx.x % n_groups;
     const long long strip = blockIdx.x / n_groups;
-    const int m0 = g * m_per_group;
-    const int mg = min(m_per_group, M - m0);
-    const int w4 = mg * dsub / 4;  // 16-byte pieces per row in this group (<= kTileConsumers)
+    const int col_lo = g * gw;
+    const int w = min(gw, M * dsub - col_lo);  // columns of this group (multiple of 4)
+    const int w4 = w / 4;                      // 16-byte pieces per row in this group (<= kTileConsumers)
 
-    float *cb = reinterpret_cast<float *>(smem_raw);                 // [mg][k][dsub]
-    uint8_t *ring = reinterpret_cast<uint8_t *>(cb + cb_floats_max);  // [kTileStages][tile_rows * M]
-    const int stage_bytes = tile_rows * M;                            // multiple of 16
-    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)kTileStages * stage_bytes);
-    uint64_t *empty = full + kTileStages;
+    float *cbt = reinterpret_cast<float *>(smem_raw);               // [k][W]
+    uint8_t *ring = reinterpret_cast<uint8_t *>(cbt + (size_t)k * W);  // [stages][tile_rows * M]
+    const int stage_bytes = tile_rows * M;                          // multiple of 16
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)stages * stage_bytes);
+    uint64_t *empty = full + stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTileStages; s++) {
+        for (int s = 0; s < stages; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kTileConsumers / 32);
         }
         fence_mbar_init();
     }
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(quantizers + (size_t)m0 * k * dsub);
-        float4 *dst = reinterpret_cast<float4 *>(cb);
-        const int total4 = mg * k * dsub / 4;
-        for (int i = threadIdx.x; i < total4; i += kTileThreads) dst[i] = __ldg(src + i);
+    for (int j = lane; j < w; j += 32) {  // column j of the group: subquantizer m, component t
+        const int gc = col_lo + j, m = gc / dsub, t = gc - m * dsub;
+        const float *src = quantizers + (size_t)m * k * dsub + t;
+        for (int c = warp; c < k; c += kTileThreads / 32) cbt[c * W + j] = __ldg(src + (size_t)c * dsub);
     }
     __syncthreads();
 
+    // strip s walks tiles tile0, tile0 + tile_step, ... (< tile1): contiguous strips (step 1) or interleaved ones
+    // (step = number of strips), where the blocks sweep the output together like one linear write stream
     const long long n_tiles = (n + tile_rows - 1) / tile_rows;
-    const long long tile0 = strip * tiles_per_strip;
-    const long long tile1 = min(n_tiles, tile0 + tiles_per_strip);
+    const long long tile0 = tile_step == 1 ? strip * tiles_per_strip : strip;
+    const long long tile1 = tile_step == 1 ? min(n_tiles, tile0 + tiles_per_strip) : n_tiles;
     const size_t total_code_bytes = (size_t)n * M;
 
     if (warp == kTileConsumers / 32) {
         // ===================== producer =====================
-        // keeps kTileStages tiles in flight; in lockstep mode the whole warp also takes part in the per-tile
+        // keeps `stages` tiles in flight; in lockstep mode the whole warp also takes part in the per-tile
         // cluster barrier (every thread of the cluster must arrive)
-        auto issue = [&](long long tile, uint32_t it) {
-            const int s = (int)(it % kTileStages);
-            mbar_wait(&empty[s], ((it / kTileStages) & 1) ^ 1);
+        int ps = 0;
+        uint32_t pph = 1;  // parity of the "empty" phase the next issue waits for
+        auto issue = [&](long long tile) {
+            mbar_wait(&empty[ps], pph);
             const size_t byte0 = (size_t)tile * stage_bytes;
             const size_t avail = total_code_bytes - byte0;
             const uint32_t bytes = (uint32_t)(avail < (size_t)stage_bytes ? avail : (size_t)stage_bytes);
             const uint32_t bulk = bytes & ~15u;
-            uint8_t *dst = ring + (size_t)s * stage_bytes;
+            uint8_t *dst = ring + (size_t)ps * stage_bytes;
             for (uint32_t b = bulk; b < bytes; b++) dst[b] = codes[byte0 + b];  // ragged end of the matrix
             if (bulk) {
-                mbar_arrive_expect_tx(&full[s], bulk);
-                bulk_g2s(dst, codes + byte0, bulk, &full[s]);
+                mbar_arrive_expect_tx(&full[ps], bulk);
+                bulk_g2s(dst, codes + byte0, bulk, &full[ps]);
             } else {
-                mbar_arrive(&full[s]);
+                mbar_arrive(&full[ps]);
+            }
+            if (++ps == stages) {
+                ps = 0;
+                pph ^= 1;
             }
         };
         if (lane == 0)
-            for (long long tile = tile0; tile < min(tile1, tile0 + kTileStages); tile++) issue(tile, (uint32_t)(tile - tile0));
-        for (long long tile = tile0; tile < tile1; tile++) {
+            for (long long tile = tile0, i = 0; tile < tile1 && i < stages; tile += tile_step, i++) issue(tile);
+        for (long long tile = tile0; tile < tile1; tile += tile_step) {
             __syncwarp();
-            if (lockstep) cluster_sync();
-            if (lane == 0 && tile + kTileStages < tile1) issue(tile + kTileStages, (uint32_t)(tile + kTileStages - tile0));
+            if (lockstep) cluster_sync_relaxed();
+            if (lane == 0 && tile + stages * tile_step < tile1) issue(tile + stages * tile_step);
         }
         return;
     }
@@ -232,52 +248,52 @@ gather_tile_kernel(const float *__restrict__ quantizers, int k, int dsub, int M,
     const int rows_par = kTileConsumers / w4;
     const int rl = (int)threadIdx.x / w4, c4 = (int)threadIdx.x % w4;
     const bool active = rl < rows_par;
-    // where this thread's two 8-byte halves come from (loop invariant)
-    const int col0 = 4 * c4, col1 = 4 * c4 + 2;
-    const int cc0 = col0 / dsub, cc1 = col1 / dsub;
-    const float *src0 = cb + cc0 * k * dsub + col0 % dsub;
-    const float *src1 = cb + cc1 * k * dsub + col1 % dsub;
-    float *ocol = out + m0 * dsub + 4 * c4;
+    // the subquantizers of this thread's two 8-byte halves (loop invariant; dsub is even, so a half never straddles)
+    const int ma = (col_lo + 4 * c4) / dsub, mb = (col_lo + 4 * c4 + 2) / dsub;
+    const bool straddle = ma != mb;
+    const float *src = cbt + 4 * c4;
+    float *ocol = out + col_lo + 4 * c4;
     bool bad = false;
 
-    uint32_t it = 0;
-    for (long long tile = tile0; tile < tile1; tile++, it++) {
-        const int s = (int)(it % kTileStages);
-        mbar_wait(&full[s], (it / kTileStages) & 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long tile = tile0; tile < tile1; tile += tile_step) {
+        mbar_wait(&full[s], ph);
         const long long r0 = tile * tile_rows;
         const int rows = (int)min((long long)tile_rows, n - r0);
         if (active) {
-            const uint8_t *crow = ring + (size_t)s * stage_bytes + m0 + rl * M;
+            const uint8_t *crow = ring + (size_t)s * stage_bytes + rl * M;
             float *op = ocol + (r0 + rl) * ldo;
             const long long ostep = (long long)rows_par * ldo;
             const int cstep = rows_par * M;
-#pragma unroll 2
+#pragma unroll kGatherUnroll
             for (int row = rl; row < rows; row += rows_par, crow += cstep, op += ostep) {
-                float4 v;
-                if constexpr (QUAD) {  // dsub % 4 == 0: the piece lies inside one centroid
-                    unsigned c = crow[cc0];
+                unsigned ca = crow[ma];
+                if constexpr (CHECK) {
+                    bad |= ca >= (unsigned)k;
+                    ca = min(ca, (unsigned)(k - 1));
+                }
+                float4 v = *reinterpret_cast<const float4 *>(src + ca * W);
+                if (straddle) {
+                    unsigned cb = crow[mb];
                     if constexpr (CHECK) {
-                        bad |= c >= (unsigned)k;
-                        c = min(c, (unsigned)(k - 1));
+                        bad |= cb >= (unsigned)k;
+                        cb = min(cb, (unsigned)(k - 1));
                     }
-                    v = *reinterpret_cast<const float4 *>(src0 + c * dsub);
-                } else {
-                    unsigned ca = crow[cc0], cbb = crow[cc1];
-                    if constexpr (CHECK) {
-                        bad |= (ca >= (unsigned)k) | (cbb >= (unsigned)k);
-                        ca = min(ca, (unsigned)(k - 1));
-                        cbb = min(cbb, (unsigned)(k - 1));
-                    }
-                    const float2 lo = *reinterpret_cast<const float2 *>(src0 + ca * dsub);
-                    const float2 hi = *reinterpret_cast<const float2 *>(src1 + cbb * dsub);
-                    v = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    const float2 hi = *reinterpret_cast<const float2 *>(src + cb * W + 2);
+                    v.z = hi.x;
+                    v.w = hi.y;
                 }
                 *reinterpret_cast<float4 *>(op) = v;
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (lockstep) cluster_sync();
+        if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+        }
+        if (lockstep) cluster_sync_relaxed();
     }
     if (bad) atomicExch(err_flag, 1);
 }
@@ -286,63 +302,75 @@ gather_tile_kernel(const float *__restrict__ quantizers, int k, int dsub, int M,
 bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, size_t n, ptrdiff_t crs, ptrdiff_t ccs,
                   float *out, ptrdiff_t ldo, int *err_flag, cudaStream_t stream, rb_status *status)
 {
-    const int M = (int)cb.M, k = (int)cb.k, dsub = (int)cb.dsub;
+    const int M = (int)cb.M, k = (int)cb.k, dsub = (int)cb.dsub, d = M * dsub;
     *status = RB_OK;
-    if (code_width != 1 || ccs != 1 || crs != (ptrdiff_t)M || (dsub & 1)) return false;
+    if (code_width != 1 || ccs != 1 || crs != (ptrdiff_t)M || (dsub & 1) || (d & 3) || k > 256) return false;
     if ((reinterpret_cast<uintptr_t>(out) & 15) || (ldo & 3) || (reinterpret_cast<uintptr_t>(codes) & 15)) return false;
-    if ((reinterpret_cast<uintptr_t>(cb.quantizers) & 15) || n < 256) return false;
-    const size_t per_m = (size_t)k * dsub * sizeof(float);
-    const int step = (dsub % 4 == 0) ? 1 : 2;  // group width must be a multiple of 4 floats
+    if (n < 256) return false;
     struct Shape {
-        int cons = 0, mg = 0, n_groups = 0, tile_rows = 0;
-        size_t cb_bytes = 0, smem = 0;
+        int cons = 0, gw = 0, W = 0, n_groups = 0, tile_rows = 0, stages = 0;
+        size_t smem = 0;
     };
-    // column groups for a block of `cons` consumers with `smem_budget` bytes of shared memory; n_groups == 0: no fit
+    static const int env_big = getenv("RB_GATHER_BIG") ? atoi(getenv("RB_GATHER_BIG")) : -1;
+    static const int env_w = getenv("RB_GATHER_W") ? atoi(getenv("RB_GATHER_W")) : 0;
+    static const int env_stages = getenv("RB_GATHER_STAGES") ? atoi(getenv("RB_GATHER_STAGES")) : 0;
+    const int stages = env_stages >= 2 && env_stages <= kMaxTileStages ? env_stages : 3;
+    // column groups for a block of `cons` consumers with `smem_budget` bytes of shared memory, of which at most
+    // `cb_budget` hold the codebook slice; n_groups == 0: no fit
     auto shape_for = [&](int cons, size_t smem_budget, size_t cb_budget) {
         Shape sh;
         sh.cons = cons;
-        int mg = (int)(cb_budget / per_m);
-        if ((size_t)mg * dsub / 4 > (size_t)cons) mg = cons * 4 / dsub;  // one 16-byte piece per thread
-        mg -= mg % step;
-        if (mg < step) return sh;
-        if (mg > M) mg = M;
-        int n_groups = (int)ceil_div(M, mg);
-        mg = (int)ceil_div(M, n_groups);
-        mg += (step - mg % step) % step;
-        n_groups = (int)ceil_div(M, mg);
-        if (((M - (n_groups - 1) * mg) * dsub) % 4 != 0) return sh;  // last group's width
-        if ((size_t)mg * k * dsub % 4 != 0 || (size_t)mg * dsub / 4 > (size_t)cons) return sh;
-        const size_t cb_bytes = (size_t)mg * per_m;
-        const size_t bar_bytes = 2 * kTileStages * sizeof(uint64_t);
-        if (cb_bytes + bar_bytes + (size_t)kTileStages * 16 * M > smem_budget) return sh;
-        int tile_rows = (int)((smem_budget - cb_bytes - bar_bytes) / kTileStages / M);
-        tile_rows -= tile_rows % 16;
+        sh.stages = stages;
+        int wmax = (int)(cb_budget / ((size_t)k * sizeof(float))) / 32 * 32;  // widest pitch that fits
+        if (wmax > cons * 4 / 32 * 32) wmax = cons * 4 / 32 * 32;              // one 16-byte piece per thread
+        if (env_w >= 32 && env_w < wmax) wmax = env_w / 32 * 32;
+        if (wmax < 32) return sh;
+        int n_groups = (int)ceil_div(d, wmax);
+        int gw = (int)ceil_div(d, n_groups);
+        gw += (4 - gw % 4) % 4;
+        // whole 128-byte lines per stripe when the rows allow it
+        if (d % 32 == 0 && (gw + 31) / 32 * 32 <= wmax && ceil_div(d, (gw + 31) / 32 * 32) == (size_t)n_groups)
+            gw = (gw + 31) / 32 * 32;
+        n_groups = (int)ceil_div(d, gw);
+        const int W = (gw + 31) / 32 * 32;
+        const size_t cb_bytes = (size_t)k * W * sizeof(float);
+        const size_t bar_bytes = 2 * stages * sizeof(uint64_t);
+        if (cb_bytes + bar_bytes + (size_t)stages * 16 * M > smem_budget) return sh;
+        int tile_rows = (int)((smem_budget - cb_bytes - bar_bytes) / stages / M);
         if (tile_rows > 256) tile_rows = 256;
-        sh.mg = mg;
+        // whole passes of the consumers over a tile (rows_par rows per pass), stage size a multiple of 16 bytes
+        const int rows_par = cons / (gw / 4);
+        int best = 0;
+        for (int t = tile_rows; t >= 8 && t > tile_rows - 4 * rows_par; t--)
+            if (((size_t)t * M) % 16 == 0 && (best == 0 || (t % rows_par == 0))) {
+                if (best == 0 || t % rows_par == 0) best = t;
+                if (t % rows_par == 0) break;
+            }
+        if (best == 0) return sh;
+        tile_rows = best;
+        sh.gw = gw;
+        sh.W = W;
         sh.n_groups = n_groups;
         sh.tile_rows = tile_rows;
-        sh.cb_bytes = cb_bytes;
-        sh.smem = cb_bytes + (size_t)kTileStages * tile_rows * M + bar_bytes;
+        sh.smem = cb_bytes + (size_t)stages * tile_rows * M + bar_bytes;
         return sh;
     };
-    Shape sh = shape_for(512, 113 * 1024, 100 * 1024);   // two blocks per SM
+    auto aligned = [&](const Shape &s) {
+        return (reinterpret_cast<uintptr_t>(out) % 128 == 0) && (ldo % 32 == 0) && (s.gw % 32 == 0);
+    };
+    Shape sh = shape_for(512, 113 * 1024, 100 * 1024);         // two blocks per SM
     const Shape big = shape_for(992, 225 * 1024, 200 * 1024);  // one block per SM
     // the big block pays off when it removes column groups whose stripes are not whole 128-byte lines
-    {
-        const bool small_aligned = sh.n_groups > 0 && (reinterpret_cast<uintptr_t>(out) % 128 == 0) && (ldo % 32 == 0) &&
-                                   ((sh.mg * dsub) % 32 == 0);
-        if (big.n_groups > 0 && (sh.n_groups == 0 || (big.n_groups < sh.n_groups && !small_aligned))) sh = big;
+    if (big.n_groups > 0 && (sh.n_groups == 0 || env_big == 1 || (big.n_groups < sh.n_groups && !aligned(sh)))) {
+        if (env_big != 0 || sh.n_groups == 0) sh = big;
     }
     if (sh.n_groups == 0) return false;
-    const int mg = sh.mg, n_groups = sh.n_groups, tile_rows = sh.tile_rows, blocks_per_sm = sh.cons == 512 ? 2 : 1;
-    const size_t cb_bytes = sh.cb_bytes, smem = sh.smem;
+    const int n_groups = sh.n_groups, tile_rows = sh.tile_rows, blocks_per_sm = sh.cons == 512 ? 2 : 1;
+    const size_t smem = sh.smem;
 
-    const bool quad = dsub % 4 == 0, check = k < 256;
-    auto kern = sh.cons == 512
-                    ? (quad ? (check ? gather_tile_kernel<true, true, 512> : gather_tile_kernel<true, false, 512>)
-                            : (check ? gather_tile_kernel<false, true, 512> : gather_tile_kernel<false, false, 512>))
-                    : (quad ? (check ? gather_tile_kernel<true, true, 992> : gather_tile_kernel<true, false, 992>)
-                            : (check ? gather_tile_kernel<false, true, 992> : gather_tile_kernel<false, false, 992>));
+    const bool check = k < 256;
+    auto kern = sh.cons == 512 ? (check ? gather_tile_kernel<true, 512> : gather_tile_kernel<false, 512>)
+                               : (check ? gather_tile_kernel<true, 992> : gather_tile_kernel<false, 992>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -352,8 +380,7 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
     // The column groups of one strip form a thread-block cluster and advance tile by tile in lockstep, so the
     // stripes of a row region reach L2 within microseconds of each other and leave it as complete lines.  Not
     // needed when every stripe segment is a whole number of 128-byte lines anyway.
-    const bool lines_aligned = (reinterpret_cast<uintptr_t>(out) % 128 == 0) && (ldo % 32 == 0) && ((mg * dsub) % 32 == 0);
-    const int lockstep = (n_groups > 1 && n_groups <= 8 && !lines_aligned) ? 1 : 0;
+    const int lockstep = (n_groups > 1 && n_groups <= 8 && !aligned(sh)) ? 1 : 0;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3((unsigned)sh.cons + 32);
     cfg.dynamicSmemBytes = smem;
@@ -383,16 +410,18 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
     strips = (n_tiles + tiles_per_strip - 1) / tiles_per_strip;
     const unsigned grid = (unsigned)(strips * n_groups);
     cfg.gridDim = dim3(grid);
+    static const int env_interleave = getenv("RB_GATHER_INTERLEAVE") ? atoi(getenv("RB_GATHER_INTERLEAVE")) : 1;
+    const long long tile_step = env_interleave ? strips : 1;
     e = cudaLaunchKernelEx(&cfg, kern, cb.quantizers, k, dsub, M, reinterpret_cast<const uint8_t *>(codes),
-                           (long long)n, out, (long long)ldo, mg, n_groups, tile_rows, tiles_per_strip,
-                           (int)(cb_bytes / sizeof(float)), err_flag, lockstep);
+                           (long long)n, out, (long long)ldo, sh.gw, n_groups, sh.W, tile_rows, sh.stages, tiles_per_strip, tile_step,
+                           err_flag, lockstep);
     if (e != cudaSuccess && lockstep) {
         // the cluster shape could not be placed (partitioned GPU, ...): same kernel without the lockstep barrier
         (void)cudaGetLastError();
         attr[0].val.clusterDim.x = 1;
         e = cudaLaunchKernelEx(&cfg, kern, cb.quantizers, k, dsub, M, reinterpret_cast<const uint8_t *>(codes),
-                               (long long)n, out, (long long)ldo, mg, n_groups, tile_rows, tiles_per_strip,
-                               (int)(cb_bytes / sizeof(float)), err_flag, 0);
+                               (long long)n, out, (long long)ldo, sh.gw, n_groups, sh.W, tile_rows, sh.stages, tiles_per_strip, tile_step,
+                               err_flag, 0);
     }
     if (e != cudaSuccess) {
         set_error("cudaLaunchKernelEx failed: %s (%s:%d)", cudaGetErrorString(e), __FILE__, __LINE__);

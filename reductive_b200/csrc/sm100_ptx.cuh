@@ -60,6 +60,12 @@ __device__ __forceinline__ void cluster_sync()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// pacing-only barrier over the cluster: no memory ordering, so outstanding global stores are not drained
+__device__ __forceinline__ void cluster_sync_relaxed()
+{
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
 // ---- proxies / bulk copies -------------------------------------------------------------------------------
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma / TMA read shared memory through it)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

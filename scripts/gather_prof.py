@@ -1,9 +1,9 @@
-"""ncu target: one reconstruct_batch per shape (C2, 1-group 400 B rows, C3)."""
+"""ncu target: one reconstruct_batch per shape (C2, C5, k = 16, C3)."""
 import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import reductive_b200 as rb
-for n, M, k, dsub in [(2_000_000, 30, 256, 10), (6_000_000, 10, 256, 10), (1_000_000, 96, 256, 8)]:
+for n, M, k, dsub in [(2_000_000, 30, 256, 10), (4_000_000, 16, 256, 8), (2_000_000, 16, 16, 8), (1_000_000, 96, 256, 8)]:
     q = np.random.default_rng(1).normal(size=(M, k, dsub)).astype(np.float32)
     pq = rb.Pq(None, q)
     g = torch.Generator(device="cuda"); g.manual_seed(3)
