@@ -63,6 +63,15 @@ typedef enum rb_encode_algo {
     RB_ENCODE_TENSOR = 2  /* tcgen05 candidate pass + exact recheck of near-ties (64 < k <= 256) */
 } rb_encode_algo;
 
+/* Which kernel applies the OPQ rotation (x.R before the argmin, .R^T after the gather; pq.rs:276,324) in the
+ * batch entry points.  Codes are bit-identical under all three; rotated reconstructions are bit-identical to the
+ * reference's FP32 GEMM under EXACT and within 1e-5 of it under TENSOR. */
+typedef enum rb_project_algo {
+    RB_PROJECT_AUTO = 0,   /* tensor path for large aligned batches, otherwise exact */
+    RB_PROJECT_EXACT = 1,  /* FP32 SIMT GEMM in the reference's summation order */
+    RB_PROJECT_TENSOR = 2  /* tcgen05 two-limb FP16 GEMM (d % 4 == 0, 32 <= d <= 4096, n >= 1024) */
+} rb_project_algo;
+
 /* Opaque product quantizer: reference `Pq<f32>` (src/pq/pq.rs:29-32) resident on one GPU. */
 typedef struct rb_pq rb_pq;
 
@@ -73,6 +82,8 @@ int rb_abi_version(void);
 uint64_t rb_kernel_launch_count(void);
 /* Process-wide default for RB_ENCODE_AUTO resolution (tests force each path). */
 rb_status rb_set_encode_algo(int algo);
+/* Process-wide choice of the rotation kernel (rb_project_algo). */
+rb_status rb_set_project_algo(int algo);
 
 /* Centroid-update summation order of the k-means entry points (process-wide).  ordered != 0 (default):
  * rows of a cluster are added sequentially in row order exactly like kmeans.rs:185-189, so sums are

@@ -5,9 +5,10 @@ include/reductive_b200.h).  There is no CPU fallback: a missing library is an Im
 is a NoDeviceError at the first compute call.
 """
 from ._cabi import (  # noqa: F401
-    ENCODE_AUTO, ENCODE_EXACT, ENCODE_TENSOR, ConstructRng, CudaError, IncorrectNAttempts, IncorrectNIterations,
+    ENCODE_AUTO, ENCODE_EXACT, ENCODE_TENSOR, PROJECT_AUTO, PROJECT_EXACT, PROJECT_TENSOR, ConstructRng, CudaError, IncorrectNAttempts, IncorrectNIterations,
     IncorrectNSubquantizerBits, IncorrectNumberSubquantizers, NoDeviceError, NSubquantizersOutsideRange,
     ReductiveError, ReductivePanic, kernel_launch_count, set_encode_algo, set_kmeans_update,
+    set_project_algo,
 )
 from .kmeans import (  # noqa: F401
     KMeans, NIterationsCondition, RandomInstanceCentroids, kmeans_iteration, kmeans_with_centroids,

@@ -31,11 +31,12 @@ ERR_UNSUPPORTED = 34
 
 MEM_HOST, MEM_DEVICE = 0, 1
 ENCODE_AUTO, ENCODE_EXACT, ENCODE_TENSOR = 0, 1, 2
+PROJECT_AUTO, PROJECT_EXACT, PROJECT_TENSOR = 0, 1, 2
 
 # every symbol include/reductive_b200.h declares (tests check the library exports each one)
 EXPORTED_SYMBOLS = [
     "rb_last_error_message", "rb_abi_version", "rb_kernel_launch_count", "rb_set_encode_algo",
-    "rb_set_kmeans_update",
+    "rb_set_kmeans_update", "rb_set_project_algo",
     "rb_pq_create", "rb_pq_destroy", "rb_pq_quantized_len", "rb_pq_reconstructed_len",
     "rb_pq_n_quantizer_centroids", "rb_pq_has_projection", "rb_pq_subquantizers", "rb_pq_projection",
     "rb_pq_quantize_batch", "rb_pq_quantize_vector", "rb_pq_reconstruct_batch", "rb_pq_reconstruct",
@@ -104,6 +105,7 @@ def _load() -> C.CDLL:
     lib.rb_kernel_launch_count.restype = C.c_uint64
     lib.rb_set_encode_algo.argtypes = [C.c_int]
     lib.rb_set_kmeans_update.argtypes = [C.c_int]
+    lib.rb_set_project_algo.argtypes = [C.c_int]
     lib.rb_pq_create.argtypes = [fp, sz, sz, sz, fp, C.POINTER(vp)]
     lib.rb_pq_destroy.argtypes = [vp]
     lib.rb_pq_destroy.restype = None
@@ -166,6 +168,11 @@ def kernel_launch_count() -> int:
 
 def set_encode_algo(algo: int) -> None:
     check(lib.rb_set_encode_algo(algo))
+
+
+def set_project_algo(algo: int) -> None:
+    """PROJECT_AUTO / PROJECT_EXACT (reference-order FP32 GEMM) / PROJECT_TENSOR (tcgen05, codes still bit-exact)."""
+    check(lib.rb_set_project_algo(algo))
 
 
 def set_kmeans_update(ordered: bool) -> None:

@@ -2,6 +2,7 @@
 // boundary, host<->device pipelines and the k-means training loop.  All arithmetic happens in the CUDA
 // kernels of this directory; there is no CPU compute path here (only copies, packing of odd strides and
 // the best-of-attempts selection on M floats).
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -10,11 +11,13 @@
 
 #include "common.cuh"
 #include "encode_tc.cuh"
+#include "project_tc.cuh"
 
 namespace rb {
 
 std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_encode_algo{RB_ENCODE_AUTO};
+static std::atomic<int> g_project_algo{RB_PROJECT_AUTO};
 static std::atomic<int> g_kmeans_ordered{1};
 static thread_local char t_err[512] = "";
 
@@ -90,6 +93,8 @@ struct rb_pq {
     float *proj_dev = nullptr;  // [d,d] or null
     float *projt_dev = nullptr; // its transpose: decode multiplies by R^T as a plain row-major matrix (same FMA order)
     TensorOperands tc;          // bf16-split codebook for the tcgen05 path (may be empty)
+    ProjTensorOperands ptc_enc, ptc_dec;  // R / R^T limbs for the tcgen05 rotation (may be empty)
+    float q_absmax = 0.f;        // max |centroid component| (bounds every gathered value); < 0: non-finite codebook
     std::vector<float> q_host, proj_host;
     DeviceCodebook cb() const { return DeviceCodebook{q_dev, cs_dev, M, k, dsub}; }
 };
@@ -137,6 +142,28 @@ static rb_status quantize_batch_device(const rb_pq *pq, const float *x, size_t n
         const float *xs = x + (ptrdiff_t)r0 * rs;
         int seq_norm = 0;
         if (pq->proj_dev) {  // pq.rs:276: rx = x.dot(projection), a fresh standard-layout array
+            // Large aligned batches: tensor-core rotation, then the tensor encode decides what is not close and
+            // re-rotates exactly what is (codes stay bit-exact, encode_tc.cuh RotatedInput).
+            const int palgo = g_project_algo.load();
+            const bool ptc_ok = cs == 1 && g_encode_algo.load() != RB_ENCODE_EXACT && pq->tc.ready() &&
+                                tensor_call_supported(cb, ws.as<float>(), rows, (ptrdiff_t)d) &&
+                                rotated_recheck_supported(cb, d) &&
+                                project_tensor_call_supported(pq->ptc_enc, xs, rows, rs, ws.as<float>(), (ptrdiff_t)d);
+            if (palgo == RB_PROJECT_TENSOR && !ptc_ok)
+                return fail(RB_ERR_UNSUPPORTED, "tensor projection does not cover this call (d=%zu, n=%zu)", d, rows);
+            if (palgo != RB_PROJECT_EXACT && ptc_ok) {
+                Workspace aux;  // [rows] per-row error bound of the rotation | scale, |x|max bits, counter, pad
+                RB_TRY(aux.alloc((rows + 4) * sizeof(float), stream));
+                float *rowerr = aux.as<float>(), *scale4 = aux.as<float>() + rows;
+                RB_TRY(launch_project_sample_scale(xs, rows, d, rs, scale4, stream));
+                RB_TRY(launch_project_tensor(pq->ptc_enc, xs, rows, rs, scale4, 0.f, ws.as<float>(), (ptrdiff_t)d, rowerr,
+                                             stream));
+                const RotatedInput rot{xs, rs, pq->proj_dev, d, rowerr, scale4, project_tensor_error_floor(pq->ptc_enc)};
+                char *cdst = reinterpret_cast<char *>(codes) + (ptrdiff_t)r0 * crs * code_width;
+                RB_TRY(launch_encode_tensor(cb, pq->tc, ws.as<float>(), rows, (ptrdiff_t)d, cdst, code_width, crs, ccs,
+                                            stream, &rot));
+                continue;
+            }
             RB_TRY(launch_project(xs, rows, d, rs, cs, pq->proj_dev, 0, ws.as<float>(), stream));
         } else {  // non-unit column stride: pack; the reference's row norms take the sequential dot then
             RB_TRY(launch_pack_rows(xs, rows, d, rs, cs, ws.as<float>(), stream));
@@ -169,7 +196,19 @@ static rb_status reconstruct_batch_device(const rb_pq *pq, const void *codes, in
         RB_TRY(launch_gather(cb, csrc, code_width, rows, crs, ccs, y.as<float>(), (ptrdiff_t)d, err_flag, stream));
         if (pq->proj_dev) {  // pq.rs:323-326: reconstructions.dot(&projection.t()), then assign
             float *pdst = direct ? odst : z.as<float>();
-            RB_TRY(launch_project(y.as<float>(), rows, d, (ptrdiff_t)d, 1, pq->projt_dev, 0, pdst, stream));
+            const ptrdiff_t pld = direct ? ors : (ptrdiff_t)d;
+            // the rotated reconstruction is allowed 1e-5 (north_star): large batches take the tensor-core GEMM
+            const int palgo = g_project_algo.load();
+            const bool ptc_ok = pq->q_absmax >= 0.f &&
+                                project_tensor_call_supported(pq->ptc_dec, y.as<float>(), rows, (ptrdiff_t)d, pdst, pld);
+            if (palgo == RB_PROJECT_TENSOR && !ptc_ok)
+                return fail(RB_ERR_UNSUPPORTED, "tensor projection does not cover this call (d=%zu, n=%zu)", d, rows);
+            if (palgo != RB_PROJECT_EXACT && ptc_ok) {
+                RB_TRY(launch_project_tensor(pq->ptc_dec, y.as<float>(), rows, (ptrdiff_t)d, nullptr,
+                                             project_scale_for_absmax(pq->q_absmax), pdst, pld, nullptr, stream));
+            } else {
+                RB_TRY(launch_project(y.as<float>(), rows, d, (ptrdiff_t)d, 1, pq->projt_dev, 0, pdst, stream));
+            }
             if (!direct) RB_TRY(launch_unpack_rows(z.as<float>(), rows, d, odst, ors, ocs, stream));
         } else {
             RB_TRY(launch_unpack_rows(y.as<float>(), rows, d, odst, ors, ocs, stream));
@@ -396,6 +435,14 @@ rb_status rb_set_encode_algo(int algo)
     return RB_OK;
 }
 
+rb_status rb_set_project_algo(int algo)
+{
+    if (algo != RB_PROJECT_AUTO && algo != RB_PROJECT_EXACT && algo != RB_PROJECT_TENSOR)
+        return fail(RB_ERR_INVALID, "unknown projection algo %d", algo);
+    g_project_algo.store(algo);
+    return RB_OK;
+}
+
 rb_status rb_set_kmeans_update(int ordered)
 {
     g_kmeans_ordered.store(ordered ? 1 : 0);
@@ -431,6 +478,18 @@ rb_status rb_pq_create(const float *quantizers, size_t M, size_t k, size_t dsub,
                 for (size_t j = 0; j < pq->d; j++) rt[j * pq->d + i] = projection[i * pq->d + j];
             RB_CUDA_TRY(cudaMalloc(&pq->projt_dev, pq->d * pq->d * sizeof(float)));
             RB_CUDA_TRY(cudaMemcpy(pq->projt_dev, rt.data(), pq->d * pq->d * sizeof(float), cudaMemcpyHostToDevice));
+            RB_TRY(pq->ptc_enc.prepare(pq->proj_dev, projection, pq->d, nullptr));
+            RB_TRY(pq->ptc_dec.prepare(pq->projt_dev, rt.data(), pq->d, nullptr));
+            float amax = 0.f;
+            for (size_t i = 0; i < qn; i++) {
+                const float a = std::fabs(quantizers[i]);
+                if (!(a <= 3.0e38f)) {  // NaN / Inf
+                    amax = -1.f;
+                    break;
+                }
+                amax = a > amax ? a : amax;
+            }
+            pq->q_absmax = amax;
         }
         RB_TRY(pq->tc.prepare(pq->cb(), nullptr));
         RB_CUDA_TRY(cudaStreamSynchronize(nullptr));
@@ -449,6 +508,8 @@ void rb_pq_destroy(rb_pq *pq)
 {
     if (!pq) return;
     pq->tc.release();
+    pq->ptc_enc.release();
+    pq->ptc_dec.release();
     cudaFree(pq->q_dev);
     cudaFree(pq->cs_dev);
     cudaFree(pq->proj_dev);

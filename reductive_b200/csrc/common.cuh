@@ -172,6 +172,13 @@ rb_status launch_encode_recheck(const DeviceCodebook &cb, const float *x, ptrdif
                                 void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs,
                                 cudaStream_t stream);
 
+// Flagged rows of a ROTATED batch, bucketed per subquantizer (counts[M], rows[M][n_cap]): re-rotate the subvector
+// exactly (reference sgemm order, x0 . r) and re-decide it with the reference's expression tree.
+bool rotated_recheck_supported(const DeviceCodebook &cb, size_t d);
+rb_status launch_rotated_recheck(const DeviceCodebook &cb, const uint32_t *counts, const uint32_t *rows, size_t n_cap,
+                                 const float *x0, ptrdiff_t ldx0, const float *r, size_t d, void *codes, int code_width,
+                                 ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream);
+
 // gather.cu — reconstruct_batch.  err_flag: device int set to 1 on an out-of-range code.
 rb_status launch_gather(const DeviceCodebook &cb, const void *codes, int code_width, size_t n,
                         ptrdiff_t crs, ptrdiff_t ccs, float *out, ptrdiff_t ldo, int *err_flag,

@@ -258,6 +258,101 @@ encode_recheck_kernel(const float *__restrict__ quantizers, const float *__restr
     }
 }
 
+// Flagged rows of a rotated batch (tensor rotation + tensor encode, encode_tc.cuh RotatedInput), bucketed per
+// subquantizer.  blockIdx.y = subquantizer m: the block keeps R[:, m*DSUB .. +DSUB) and the m-th codebook in shared
+// memory and walks its share of the bucket, thread = flagged row:
+//   rx_sub = x0_row . R[:, cols]   one FMA chain per component over K blocks of 256 combined by a plain add
+//                                  (matrixmultiply's order, as project.cu) -> the bits the reference's rx holds
+//   code   = the reference's argmin over the k centroids (same expression tree as encode_exact_kernel)
+template <int DSUB>
+__global__ void __launch_bounds__(256)
+rotated_recheck_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ rows, long long n_cap,
+                       const float *__restrict__ x0, long long ldx0, const float *__restrict__ r, int d,
+                       const float *__restrict__ quantizers, const float *__restrict__ cs_all, int k, void *codes,
+                       int code_width, long long crs, long long ccs)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int m = blockIdx.y;
+    const uint32_t cnt = (uint32_t)min((long long)counts[m], n_cap);
+    if ((uint32_t)blockIdx.x * 256u >= cnt) return;
+    float *rs = smem;                    // [d][DSUB]
+    float *cen = rs + (size_t)d * DSUB;  // [k][DSUB]
+    float *csm = cen + (size_t)k * DSUB; // [k]
+    const float *qm = quantizers + (size_t)m * k * DSUB;
+    const float *csg = cs_all + (size_t)m * k;
+    for (int i = threadIdx.x; i < d * DSUB; i += 256) {
+        const int ii = i / DSUB, t = i - ii * DSUB;
+        rs[i] = __ldg(r + (size_t)ii * d + m * DSUB + t);
+    }
+    for (int i = threadIdx.x; i < k * DSUB; i += 256) cen[i] = __ldg(qm + i);
+    for (int i = threadIdx.x; i < k; i += 256) csm[i] = __ldg(csg + i);
+    __syncthreads();
+    for (uint32_t base = blockIdx.x * 256u; base < cnt; base += gridDim.x * 256u) {
+        const uint32_t idx = base + threadIdx.x;
+        if (idx >= cnt) continue;
+        const long long row = rows[(size_t)m * (size_t)n_cap + idx];
+        const float *xr = x0 + row * ldx0;
+        float rx[DSUB];
+        for (int i0 = 0; i0 < d; i0 += 256) {
+            float acc[DSUB];
+#pragma unroll
+            for (int t = 0; t < DSUB; t++) acc[t] = 0.f;
+            const int i1 = min(d, i0 + 256);
+            for (int i = i0; i < i1; i += 4) {  // d % 4 == 0, 16-byte aligned rows (project_tensor_call_supported)
+                const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr + i));
+                const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    float c[DSUB];
+                    load_centroid<DSUB>(rs + (size_t)(i + e) * DSUB, c);
+#pragma unroll
+                    for (int t = 0; t < DSUB; t++) acc[t] = __fmaf_rn(xe[e], c[t], acc[t]);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < DSUB; t++) rx[t] = i0 == 0 ? acc[t] : __fadd_rn(rx[t], acc[t]);
+        }
+        const float xs = unrolled_sqnorm_reg<DSUB>(rx);
+        float best = __int_as_float(0x7f800000);
+        int bidx = kInvalid;
+#pragma unroll 2
+        for (int j = 0; j < k; j++) {
+            float c[DSUB];
+            load_centroid<DSUB>(cen + (size_t)j * DSUB, c);
+            float dp = 0.f;
+#pragma unroll
+            for (int t = 0; t < DSUB; t++) dp = __fmaf_rn(rx[t], c[t], dp);
+            const float dist = ref_distance(xs, csm[j], dp);
+            if (dist < best) {
+                best = dist;
+                bidx = j;
+            }
+        }
+        if (bidx == kInvalid) bidx = slow_argmin<DSUB>(qm, csg, k, rx, xs);
+        store_code(codes, code_width, row * crs + (long long)m * ccs, (unsigned)bidx);
+    }
+}
+
+template <int DSUB>
+rb_status launch_rotated_t(const DeviceCodebook &cb, const uint32_t *counts, const uint32_t *rows, size_t n_cap,
+                           const float *x0, ptrdiff_t ldx0, const float *r, size_t d, void *codes, int code_width,
+                           ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream)
+{
+    const size_t smem = (d * DSUB + cb.k * DSUB + cb.k) * sizeof(float);
+    auto kern = rotated_recheck_kernel<DSUB>;
+    if (smem > 48 * 1024) RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // a few blocks per subquantizer, each staging its operands once; about four blocks' worth of work per SM
+    unsigned per_m = (unsigned)ceil_div((size_t)148 * 4, cb.M);
+    const unsigned most = (unsigned)ceil_div(n_cap, (size_t)256);
+    if (per_m > most) per_m = most;
+    if (per_m < 1) per_m = 1;
+    kern<<<dim3(per_m, (unsigned)cb.M), 256, smem, stream>>>(counts, rows, (long long)n_cap, x0, (long long)ldx0, r, (int)d,
+                                                             cb.quantizers, cb.cs, (int)cb.k, codes, code_width,
+                                                             (long long)crs, (long long)ccs);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
 template <int DSUB>
 rb_status launch_t(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t ldx, void *codes, int code_width,
                    ptrdiff_t crs, ptrdiff_t ccs, int seq_norm, const uint32_t *gate, uint32_t gate_thr, cudaStream_t stream)
@@ -325,6 +420,38 @@ rb_status launch_centroid_norms(const float *quantizers, size_t rows, size_t dsu
     centroid_norms_kernel<<<(unsigned)ceil_div(rows, 128), 128, 0, stream>>>(quantizers, rows, (int)dsub, cs);
     RB_LAUNCH_CHECK();
     return RB_OK;
+}
+
+// the subvector widths the tensor encode is instantiated for (encode_tc.cu RB_TC_DSUBS)
+#define RB_ROT_DSUBS(X) X(2) X(4) X(6) X(8) X(10) X(12) X(16) X(20) X(24) X(30) X(32)
+
+bool rotated_recheck_supported(const DeviceCodebook &cb, size_t d)
+{
+    if (cb.M > 65535 || d != cb.M * cb.dsub) return false;
+    if ((d * cb.dsub + cb.k * cb.dsub + cb.k) * sizeof(float) > 200 * 1024) return false;
+    switch (cb.dsub) {
+#define X(D) case D:
+        RB_ROT_DSUBS(X)
+#undef X
+        return true;
+    default: return false;
+    }
+}
+
+rb_status launch_rotated_recheck(const DeviceCodebook &cb, const uint32_t *counts, const uint32_t *rows, size_t n_cap,
+                                 const float *x0, ptrdiff_t ldx0, const float *r, size_t d, void *codes, int code_width,
+                                 ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream)
+{
+    switch (cb.dsub) {
+#define X(D)                                                                                                             \
+    case D:                                                                                                              \
+        return launch_rotated_t<D>(cb, counts, rows, n_cap, x0, ldx0, r, d, codes, code_width, crs, ccs, stream);
+        RB_ROT_DSUBS(X)
+#undef X
+    default: break;
+    }
+    set_error("rotated recheck: subvector width %zu is not instantiated", cb.dsub);
+    return RB_ERR_UNSUPPORTED;
 }
 
 rb_status launch_encode_recheck(const DeviceCodebook &cb, const float *x, ptrdiff_t ldx, const uint32_t *pairs,

@@ -175,6 +175,12 @@ struct EncParams {
     uint32_t max_pairs;
     int M, gm, n_groups, a_stages, pitch_f;
     float xs_limit;  // rows with ||x * scale||^2 at or above this are decided exactly
+    // x is an APPROXIMATE rotation of other rows (project_tc.cu): every component of a row may be off by
+    // rowerr[row] + perr_floor / *perr_sx, which widens the margin; rowerr == nullptr: x is exact
+    uint32_t *bucket_counts, *bucket_rows;  // rotated input: flagged rows per subquantizer, [M] and [M][n]
+    const float *rowerr;
+    const float *perr_sx;  // device scalar: the rotation's operand scale
+    float perr_floor;
     long long n_tiles;
     long long *trace;  // debugging aid (RB_TC_TRACE): per-role clock64 stamps of CTA 0, else nullptr
     unsigned short cta_start[kMaxGroups + 1];  // CTAs [cta_start[g], cta_start[g+1]) own column group g
@@ -356,6 +362,11 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
             mbar_wait(&x_full[stage], (li >> 1) & 1);
             RB_PH(1);
             const float4 *xr = reinterpret_cast<const float4 *>(sX + (size_t)stage * xs_bytes + (size_t)row * p.pitch_f * 4);
+            float perr = 0.f;  // bound on the error of each component of this row (0: the row is exact)
+            if (p.rowerr != nullptr) {
+                const long long grow = t * kTile + row;
+                perr = (grow < p.n ? p.rowerr[grow] : 0.f) + p.perr_floor / p.perr_sx[0];
+            }
             // two subquantizers at a time: 2*DSUB floats are a whole number of 16-byte vectors, and with a row pitch
             // that is an odd multiple of 16 bytes the 128-bit loads of a warp are bank-conflict free
             for (int ml0 = 0; ml0 < gm_cur; ml0 += 2) {
@@ -404,7 +415,8 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     const float xs_sc = xs * scale2;
                     const bool bad = cb_bad || !(xs_sc < p.xs_limit);
                     const float csmax = p.consts[g * p.gm + ml0 + h];
-                    float marg = margin_of(xs, csmax, DSUB) * scale2;
+                    // a component error of perr moves a score 2 x.c by at most 2 sqrt(dsub) perr ||c||; margin = 2 x bound
+                    float marg = (margin_of(xs, csmax, DSUB) + 4.0f * perr * sqrtf((float)DSUB * csmax)) * scale2;
                     if (bad || !(marg < 3.0e38f)) marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
                     RB_PH(2);
                     mbar_wait(&a_empty[as], aph ^ 1);
@@ -505,10 +517,15 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     const unsigned code = certain ? (unsigned)(int)fmaf(accb - 64.f, 16.f, acca - 64.f) : 0u;
                     store_code(p.codes, p.code_width, grow * p.crs + (long long)m * p.ccs, code);
                     if (!certain) {
-                        const uint32_t slot = atomicAdd(p.n_pairs, 1u);
-                        if (slot < p.max_pairs) {
-                            p.pairs[2 * (size_t)slot] = (uint32_t)grow;
-                            p.pairs[2 * (size_t)slot + 1] = (uint32_t)m;
+                        if (p.bucket_rows != nullptr) {  // a row is flagged at most once per subquantizer: slot < n
+                            const uint32_t slot = atomicAdd(&p.bucket_counts[m], 1u);
+                            p.bucket_rows[(size_t)m * (size_t)p.n + slot] = (uint32_t)grow;
+                        } else {
+                            const uint32_t slot = atomicAdd(p.n_pairs, 1u);
+                            if (slot < p.max_pairs) {
+                                p.pairs[2 * (size_t)slot] = (uint32_t)grow;
+                                p.pairs[2 * (size_t)slot + 1] = (uint32_t)m;
+                            }
                         }
                     }
                 }
@@ -639,7 +656,7 @@ int device_sm_count()
 template <int DSUB>
 rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const float *x, size_t n, ptrdiff_t ldx, void *codes,
                    int code_width, ptrdiff_t crs, ptrdiff_t ccs, uint32_t *pairs, uint32_t *n_pairs, uint32_t max_pairs,
-                   cudaStream_t stream)
+                   const RotatedInput *rot, cudaStream_t stream)
 {
     const size_t n_tiles = ceil_div(n, (size_t)kTile);
     const Plan plan = make_plan(cb.M, cb.dsub, n_tiles, device_sm_count());
@@ -663,6 +680,11 @@ rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const flo
     p.n_tiles = (long long)n_tiles;
     p.xs_limit = cb.k < (size_t)kCent ? 1.0e6f : 1.0e9f;
     p.trace = nullptr;
+    p.bucket_counts = rot ? n_pairs : nullptr;
+    p.bucket_rows = rot ? pairs : nullptr;
+    p.rowerr = rot ? rot->rowerr : nullptr;
+    p.perr_sx = rot ? rot->sx_dev : nullptr;
+    p.perr_floor = rot ? rot->err_floor : 0.f;
     for (int g = 0; g <= kMaxGroups; g++) p.cta_start[g] = plan.cta_start[g < plan.n_groups ? g : plan.n_groups];
     CUtensorMap tmap;
     RB_TRY(make_x_tensor_map(x, n, cb.M * cb.dsub, ldx, (size_t)plan.pitch_f, &tmap));
@@ -797,7 +819,8 @@ void TensorOperands::release_async(cudaStream_t stream)
 }
 
 rb_status launch_encode_tensor(const DeviceCodebook &cb, const TensorOperands &tc, const float *x, size_t n, ptrdiff_t ldx,
-                               void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream)
+                               void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream,
+                               const RotatedInput *rot)
 {
     if (n == 0) return RB_OK;
     if (!tc.ready() || !tensor_call_supported(cb, x, n, ldx)) {
@@ -807,18 +830,57 @@ rb_status launch_encode_tensor(const DeviceCodebook &cb, const TensorOperands &t
     // list of (row, subquantizer) pairs the tensor pass could not decide; when it overflows the whole batch is
     // re-encoded by the exact kernel (gated on the device, no host round trip)
     const size_t units = n * cb.M;
+    uint32_t *work = nullptr;
+    rb_status st = RB_OK;
+    if (rot) {
+        // A rotated input cannot fall back to the exact kernel on the same (approximate) buffer.  The flagged rows
+        // are collected per subquantizer, [M] counters + [M][n] row indices, and re-decided by a kernel that first
+        // re-rotates the subvector exactly (encode_exact.cu).
+        if (n > 0xffffffffull || !rotated_recheck_supported(cb, rot->d)) {
+            set_error("tensor encode of a rotated batch does not cover this shape (n=%zu, d=%zu)", n, rot->d);
+            return RB_ERR_UNSUPPORTED;
+        }
+        const size_t counters = (cb.M + 3) / 4 * 4;
+        RB_CUDA_TRY(cudaMallocAsync(&work, (counters + units) * sizeof(uint32_t), stream));
+        uint32_t *counts = work, *rows = work + counters;
+        auto body = [&]() -> rb_status {
+            RB_CUDA_TRY(cudaMemsetAsync(counts, 0, counters * sizeof(uint32_t), stream));
+            switch (cb.dsub) {
+#define X(D)                                                                                                         \
+    case D:                                                                                                          \
+        RB_TRY(launch_t<D>(cb, tc, x, n, ldx, codes, code_width, crs, ccs, rows, counts, 0u, rot, stream));           \
+        break;
+                RB_TC_DSUBS(X)
+#undef X
+            default: break;
+            }
+            if (getenv("RB_TC_STATS")) {
+                std::vector<uint32_t> h(cb.M);
+                RB_CUDA_TRY(cudaMemcpyAsync(h.data(), counts, cb.M * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+                RB_CUDA_TRY(cudaStreamSynchronize(stream));
+                size_t tot = 0;
+                for (uint32_t c : h) tot += c;
+                fprintf(stderr, "[rb tc] rotated n=%zu M=%zu dsub=%zu: %zu of %zu pairs re-rotated and re-decided exactly (%.4f%%)\n",
+                        n, cb.M, cb.dsub, tot, units, 100.0 * tot / (double)units);
+            }
+            return launch_rotated_recheck(cb, counts, rows, n, rot->x0, rot->ldx0, rot->r, rot->d, codes, code_width, crs, ccs,
+                                          stream);
+        };
+        st = body();
+        cudaFreeAsync(work, stream);
+        return st;
+    }
     size_t cap = units / 8 + 4096;
     if (cap > 0x7fffffffull) cap = 0x7fffffffull;
-    uint32_t *work = nullptr;
     RB_CUDA_TRY(cudaMallocAsync(&work, (2 * cap + 4) * sizeof(uint32_t), stream));
     uint32_t *n_pairs = work, *pairs = work + 4;
-    rb_status st = RB_OK;
     auto body = [&]() -> rb_status {
         RB_CUDA_TRY(cudaMemsetAsync(n_pairs, 0, 4 * sizeof(uint32_t), stream));
         switch (cb.dsub) {
 #define X(D)                                                                                                         \
     case D:                                                                                                          \
-        RB_TRY(launch_t<D>(cb, tc, x, n, ldx, codes, code_width, crs, ccs, pairs, n_pairs, (uint32_t)cap, stream));  \
+        RB_TRY(launch_t<D>(cb, tc, x, n, ldx, codes, code_width, crs, ccs, pairs, n_pairs, (uint32_t)cap, nullptr,   \
+                           stream));                                                                                 \
         break;
             RB_TC_DSUBS(X)
 #undef X
