@@ -82,6 +82,9 @@ int rb_abi_version(void);
 uint64_t rb_kernel_launch_count(void);
 /* Process-wide default for RB_ENCODE_AUTO resolution (tests force each path). */
 rb_status rb_set_encode_algo(int algo);
+/* Scratch buffers (workspaces, flagged-pair lists, sort buffers) come from a per-device memory pool the library
+ * keeps across calls; this hands the unused part back to the driver (current device). */
+rb_status rb_release_scratch(void);
 /* Process-wide choice of the rotation kernel (rb_project_algo). */
 rb_status rb_set_project_algo(int algo);
 

@@ -36,7 +36,7 @@ PROJECT_AUTO, PROJECT_EXACT, PROJECT_TENSOR = 0, 1, 2
 # every symbol include/reductive_b200.h declares (tests check the library exports each one)
 EXPORTED_SYMBOLS = [
     "rb_last_error_message", "rb_abi_version", "rb_kernel_launch_count", "rb_set_encode_algo",
-    "rb_set_kmeans_update", "rb_set_project_algo",
+    "rb_set_kmeans_update", "rb_set_project_algo", "rb_release_scratch",
     "rb_pq_create", "rb_pq_destroy", "rb_pq_quantized_len", "rb_pq_reconstructed_len",
     "rb_pq_n_quantizer_centroids", "rb_pq_has_projection", "rb_pq_subquantizers", "rb_pq_projection",
     "rb_pq_quantize_batch", "rb_pq_quantize_vector", "rb_pq_reconstruct_batch", "rb_pq_reconstruct",
@@ -168,6 +168,11 @@ def kernel_launch_count() -> int:
 
 def set_encode_algo(algo: int) -> None:
     check(lib.rb_set_encode_algo(algo))
+
+
+def release_scratch() -> None:
+    """Hand the library's cached scratch memory (current device) back to the driver."""
+    check(lib.rb_release_scratch())
 
 
 def set_project_algo(algo: int) -> None:

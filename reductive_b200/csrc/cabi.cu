@@ -29,6 +29,34 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {};
+
+cudaError_t pool_malloc(void **p, size_t bytes, cudaStream_t stream)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(p, bytes, stream);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if (!g_pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            e = cudaMemPoolCreate(&g_pools[dev], &props);
+            if (e != cudaSuccess) return e;
+            unsigned long long keep = ~0ull;  // keep everything until rb_release_scratch
+            cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool = g_pools[dev];
+    }
+    return cudaMallocFromPoolAsync(p, bytes, pool, stream);
+}
+
 static rb_status fail(rb_status s, const char *fmt, ...)
 {
     va_list ap;
@@ -70,7 +98,7 @@ struct Workspace {
     rb_status alloc(size_t bytes, cudaStream_t stream)
     {
         s = stream;
-        RB_CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 1, stream));
+        RB_CUDA_TRY(pool_malloc((void **)&p, bytes ? bytes : 1, stream));
         return RB_OK;
     }
     ~Workspace()
@@ -147,7 +175,7 @@ static rb_status quantize_batch_device(const rb_pq *pq, const float *x, size_t n
             const int palgo = g_project_algo.load();
             const bool ptc_ok = cs == 1 && g_encode_algo.load() != RB_ENCODE_EXACT && pq->tc.ready() &&
                                 tensor_call_supported(cb, ws.as<float>(), rows, (ptrdiff_t)d) &&
-                                rotated_recheck_supported(cb, d) &&
+                                rotated_recheck_supported(cb, d) && project_tensor_rowerr_supported(pq->ptc_enc) &&
                                 project_tensor_call_supported(pq->ptc_enc, xs, rows, rs, ws.as<float>(), (ptrdiff_t)d);
             if (palgo == RB_PROJECT_TENSOR && !ptc_ok)
                 return fail(RB_ERR_UNSUPPORTED, "tensor projection does not cover this call (d=%zu, n=%zu)", d, rows);
@@ -432,6 +460,15 @@ rb_status rb_set_encode_algo(int algo)
     if (algo != RB_ENCODE_AUTO && algo != RB_ENCODE_EXACT && algo != RB_ENCODE_TENSOR)
         return fail(RB_ERR_INVALID, "unknown encode algo %d", algo);
     g_encode_algo.store(algo);
+    return RB_OK;
+}
+
+rb_status rb_release_scratch(void)
+{
+    int dev = 0;
+    RB_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (dev >= 0 && dev < 64 && g_pools[dev]) RB_CUDA_TRY(cudaMemPoolTrimTo(g_pools[dev], 0));
     return RB_OK;
 }
 

@@ -16,6 +16,10 @@ namespace rb {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+// Stream-ordered scratch allocation from the library's own memory pool (one per device, never trimmed at
+// synchronisation points: the default pool hands its memory back to the driver at every sync, which costs a
+// ~0.5 ms re-allocation in the first call after each one).  Free with cudaFreeAsync.
+cudaError_t pool_malloc(void **p, size_t bytes, cudaStream_t stream);
 
 #define RB_CUDA_TRY(expr)                                                                        \
     do {                                                                                         \

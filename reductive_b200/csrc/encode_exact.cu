@@ -274,7 +274,7 @@ rotated_recheck_kernel(const uint32_t *__restrict__ counts, const uint32_t *__re
     extern __shared__ __align__(16) float smem[];
     const int m = blockIdx.y;
     const uint32_t cnt = (uint32_t)min((long long)counts[m], n_cap);
-    if ((uint32_t)blockIdx.x * 256u >= cnt) return;
+    if ((uint32_t)blockIdx.x * 256u * (DSUB <= 16 ? 2u : 1u) >= cnt) return;
     float *rs = smem;                    // [d][DSUB]
     float *cen = rs + (size_t)d * DSUB;  // [k][DSUB]
     float *csm = cen + (size_t)k * DSUB; // [k]
@@ -287,49 +287,81 @@ rotated_recheck_kernel(const uint32_t *__restrict__ counts, const uint32_t *__re
     for (int i = threadIdx.x; i < k * DSUB; i += 256) cen[i] = __ldg(qm + i);
     for (int i = threadIdx.x; i < k; i += 256) csm[i] = __ldg(csg + i);
     __syncthreads();
-    for (uint32_t base = blockIdx.x * 256u; base < cnt; base += gridDim.x * 256u) {
-        const uint32_t idx = base + threadIdx.x;
-        if (idx >= cnt) continue;
-        const long long row = rows[(size_t)m * (size_t)n_cap + idx];
-        const float *xr = x0 + row * ldx0;
-        float rx[DSUB];
-        for (int i0 = 0; i0 < d; i0 += 256) {
-            float acc[DSUB];
+    // RPT flagged rows per thread: every shared-memory operand read (a row of R, a centroid) feeds RPT FMA chains
+    constexpr int RPT = DSUB <= 16 ? 2 : 1;
+    for (uint32_t base = blockIdx.x * (256u * RPT); base < cnt; base += gridDim.x * (256u * RPT)) {
+        long long row[RPT];
+        const float *xr[RPT];
+        bool live[RPT];
 #pragma unroll
-            for (int t = 0; t < DSUB; t++) acc[t] = 0.f;
+        for (int q = 0; q < RPT; q++) {
+            const uint32_t idx = base + q * 256u + threadIdx.x;
+            live[q] = idx < cnt;
+            row[q] = rows[(size_t)m * (size_t)n_cap + (live[q] ? idx : base)];  // base < cnt: a valid slot
+            xr[q] = x0 + row[q] * ldx0;
+        }
+        float rx[RPT][DSUB];
+        for (int i0 = 0; i0 < d; i0 += 256) {
+            float acc[RPT][DSUB];
+#pragma unroll
+            for (int q = 0; q < RPT; q++)
+#pragma unroll
+                for (int t = 0; t < DSUB; t++) acc[q][t] = 0.f;
             const int i1 = min(d, i0 + 256);
             for (int i = i0; i < i1; i += 4) {  // d % 4 == 0, 16-byte aligned rows (project_tensor_call_supported)
-                const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr + i));
-                const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+                float xe[RPT][4];
+#pragma unroll
+                for (int q = 0; q < RPT; q++) {
+                    const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr[q] + i));
+                    xe[q][0] = xv.x; xe[q][1] = xv.y; xe[q][2] = xv.z; xe[q][3] = xv.w;
+                }
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     float c[DSUB];
                     load_centroid<DSUB>(rs + (size_t)(i + e) * DSUB, c);
 #pragma unroll
-                    for (int t = 0; t < DSUB; t++) acc[t] = __fmaf_rn(xe[e], c[t], acc[t]);
+                    for (int q = 0; q < RPT; q++)
+#pragma unroll
+                        for (int t = 0; t < DSUB; t++) acc[q][t] = __fmaf_rn(xe[q][e], c[t], acc[q][t]);
                 }
             }
 #pragma unroll
-            for (int t = 0; t < DSUB; t++) rx[t] = i0 == 0 ? acc[t] : __fadd_rn(rx[t], acc[t]);
+            for (int q = 0; q < RPT; q++)
+#pragma unroll
+                for (int t = 0; t < DSUB; t++) rx[q][t] = i0 == 0 ? acc[q][t] : __fadd_rn(rx[q][t], acc[q][t]);
         }
-        const float xs = unrolled_sqnorm_reg<DSUB>(rx);
-        float best = __int_as_float(0x7f800000);
-        int bidx = kInvalid;
+        float xs[RPT], best[RPT];
+        int bidx[RPT];
+#pragma unroll
+        for (int q = 0; q < RPT; q++) {
+            xs[q] = unrolled_sqnorm_reg<DSUB>(rx[q]);
+            best[q] = __int_as_float(0x7f800000);
+            bidx[q] = kInvalid;
+        }
 #pragma unroll 2
         for (int j = 0; j < k; j++) {
             float c[DSUB];
             load_centroid<DSUB>(cen + (size_t)j * DSUB, c);
-            float dp = 0.f;
+            const float csj = csm[j];
 #pragma unroll
-            for (int t = 0; t < DSUB; t++) dp = __fmaf_rn(rx[t], c[t], dp);
-            const float dist = ref_distance(xs, csm[j], dp);
-            if (dist < best) {
-                best = dist;
-                bidx = j;
+            for (int q = 0; q < RPT; q++) {
+                float dp = 0.f;
+#pragma unroll
+                for (int t = 0; t < DSUB; t++) dp = __fmaf_rn(rx[q][t], c[t], dp);
+                const float dist = ref_distance(xs[q], csj, dp);
+                if (dist < best[q]) {
+                    best[q] = dist;
+                    bidx[q] = j;
+                }
             }
         }
-        if (bidx == kInvalid) bidx = slow_argmin<DSUB>(qm, csg, k, rx, xs);
-        store_code(codes, code_width, row * crs + (long long)m * ccs, (unsigned)bidx);
+#pragma unroll
+        for (int q = 0; q < RPT; q++) {
+            if (!live[q]) continue;
+            int bi = bidx[q];
+            if (bi == kInvalid) bi = slow_argmin<DSUB>(qm, csg, k, rx[q], xs[q]);
+            store_code(codes, code_width, row[q] * crs + (long long)m * ccs, (unsigned)bi);
+        }
     }
 }
 

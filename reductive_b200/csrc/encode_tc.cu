@@ -38,6 +38,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "encode_tc.cuh"
@@ -416,7 +417,9 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     const bool bad = cb_bad || !(xs_sc < p.xs_limit);
                     const float csmax = p.consts[g * p.gm + ml0 + h];
                     // a component error of perr moves a score 2 x.c by at most 2 sqrt(dsub) perr ||c||; margin = 2 x bound
-                    float marg = (margin_of(xs, csmax, DSUB) + 4.0f * perr * sqrtf((float)DSUB * csmax)) * scale2;
+                    float marg = margin_of(xs, csmax, DSUB);
+                    if (p.rowerr != nullptr) marg += 4.0f * perr * sqrtf((float)DSUB * csmax);
+                    marg *= scale2;
                     if (bad || !(marg < 3.0e38f)) marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
                     RB_PH(2);
                     mbar_wait(&a_empty[as], aph ^ 1);
@@ -557,7 +560,32 @@ struct Plan {
 // Column grouping and CTA allocation.  A CTA keeps the B operands of one group of gm subquantizers in shared
 // memory for its whole life and walks 128-row tiles; groups get CTAs in proportion to their width.  Chosen to
 // minimise the busiest CTA's number of (tile, subquantizer) units.
+Plan make_plan_uncached(size_t M, size_t dsub, size_t n_tiles, int sms);
+
+// The search below costs 40-250 us of host time (it is quadratic in the number of column groups), which shows in
+// loops of short calls (k-means on small row counts): the last few shapes are remembered.
 Plan make_plan(size_t M, size_t dsub, size_t n_tiles, int sms)
+{
+    struct Entry {
+        size_t M, dsub, n_tiles;
+        int sms;
+        Plan plan;
+    };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const Entry &e : cache)
+            if (e.M == M && e.dsub == dsub && e.n_tiles == n_tiles && e.sms == sms) return e.plan;
+    }
+    const Plan plan = make_plan_uncached(M, dsub, n_tiles, sms);
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() >= 32) cache.erase(cache.begin());
+    cache.push_back(Entry{M, dsub, n_tiles, sms, plan});
+    return plan;
+}
+
+Plan make_plan_uncached(size_t M, size_t dsub, size_t n_tiles, int sms)
 {
     Plan best;
     unsigned long long best_span = ~0ull;
@@ -782,7 +810,7 @@ rb_status TensorOperands::prepare(const DeviceCodebook &cb, cudaStream_t stream)
     const size_t b_bytes = cb.M * (size_t)(kpad / 8) * kCent * 16;
     const size_t c_bytes = (cb.M + 4) * sizeof(float);
     if (!b_tiles) {
-        RB_CUDA_TRY(cudaMallocAsync(&b_tiles, b_bytes + c_bytes, stream));
+        RB_CUDA_TRY(pool_malloc((void **)&b_tiles, b_bytes + c_bytes, stream));
         bytes = b_bytes + c_bytes;
     }
     consts = reinterpret_cast<float *>(reinterpret_cast<char *>(b_tiles) + b_bytes);
@@ -841,7 +869,7 @@ rb_status launch_encode_tensor(const DeviceCodebook &cb, const TensorOperands &t
             return RB_ERR_UNSUPPORTED;
         }
         const size_t counters = (cb.M + 3) / 4 * 4;
-        RB_CUDA_TRY(cudaMallocAsync(&work, (counters + units) * sizeof(uint32_t), stream));
+        RB_CUDA_TRY(pool_malloc((void **)&work, (counters + units) * sizeof(uint32_t), stream));
         uint32_t *counts = work, *rows = work + counters;
         auto body = [&]() -> rb_status {
             RB_CUDA_TRY(cudaMemsetAsync(counts, 0, counters * sizeof(uint32_t), stream));
@@ -872,7 +900,7 @@ rb_status launch_encode_tensor(const DeviceCodebook &cb, const TensorOperands &t
     }
     size_t cap = units / 8 + 4096;
     if (cap > 0x7fffffffull) cap = 0x7fffffffull;
-    RB_CUDA_TRY(cudaMallocAsync(&work, (2 * cap + 4) * sizeof(uint32_t), stream));
+    RB_CUDA_TRY(pool_malloc((void **)&work, (2 * cap + 4) * sizeof(uint32_t), stream));
     uint32_t *n_pairs = work, *pairs = work + 4;
     auto body = [&]() -> rb_status {
         RB_CUDA_TRY(cudaMemsetAsync(n_pairs, 0, 4 * sizeof(uint32_t), stream));

@@ -471,8 +471,8 @@ rb_status launch_ordered_fast(const float *x, size_t n, ptrdiff_t ldx, const uin
     const size_t n_chunks = ceil_div(n, (size_t)kChunkRows);
     uint16_t *list = nullptr;
     uint32_t *lstart = nullptr;
-    RB_CUDA_TRY(cudaMallocAsync(&list, M * n_chunks * kChunkRows * sizeof(uint16_t), stream));
-    RB_CUDA_TRY(cudaMallocAsync(&lstart, n_chunks * M * (k + 1) * sizeof(uint32_t), stream));
+    RB_CUDA_TRY(pool_malloc((void **)&list, M * n_chunks * kChunkRows * sizeof(uint16_t), stream));
+    RB_CUDA_TRY(pool_malloc((void **)&lstart, n_chunks * M * (k + 1) * sizeof(uint32_t), stream));
     rb_status st = RB_OK;
     auto body = [&]() -> rb_status {
         const size_t smem = kChunkRows + (size_t)kChunkRows * 2 + (size_t)kLocalWarps * k * 4 + (k + 1) * 4;
@@ -581,10 +581,10 @@ rb_status launch_ordered_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT 
     n_chunks = ceil_div(n, rows_per_chunk);
     const size_t pairs = n_chunks * M;
     unsigned *cnt = nullptr, *total = nullptr, *base = nullptr, *list = nullptr;
-    RB_CUDA_TRY(cudaMallocAsync(&cnt, pairs * k * sizeof(unsigned), stream));
-    RB_CUDA_TRY(cudaMallocAsync(&total, M * k * sizeof(unsigned), stream));
-    RB_CUDA_TRY(cudaMallocAsync(&base, M * k * sizeof(unsigned), stream));
-    RB_CUDA_TRY(cudaMallocAsync(&list, M * n * sizeof(unsigned), stream));
+    RB_CUDA_TRY(pool_malloc((void **)&cnt, pairs * k * sizeof(unsigned), stream));
+    RB_CUDA_TRY(pool_malloc((void **)&total, M * k * sizeof(unsigned), stream));
+    RB_CUDA_TRY(pool_malloc((void **)&base, M * k * sizeof(unsigned), stream));
+    RB_CUDA_TRY(pool_malloc((void **)&list, M * n * sizeof(unsigned), stream));
     const size_t smem = (size_t)kSortWarps * k * sizeof(unsigned);
     const unsigned blocks = (unsigned)ceil_div(pairs, kSortWarps);
     rb_status st = RB_OK;

@@ -17,10 +17,11 @@
 //
 // Work split: unit = (128-row tile, group of NT <= 256 output columns); persistent CTAs walk the units with the
 // groups of one tile adjacent, so x is read from HBM once.  Per unit the K loop runs over chunks of 32 x-columns:
-//   warp 9      x producer: one TMA tensor-map box (128 rows x 36 floats, pitch an odd multiple of 16 B) per chunk
-//   warp 10     B producer: the chunk's pre-split R limbs (core-matrix layout, one contiguous cp.async.bulk)
-//   warps 4-7   converters (thread = row): FP32 -> two FP16 limbs, K-major core-matrix A operand, row norm
-//   warp 8      one thread issues 6 tcgen05.mma (M128 x NT x K16) per chunk and the commits
+//   warp 13     x producer: one TMA tensor-map box (128 rows x 36 floats, pitch an odd multiple of 16 B) per chunk
+//   warp 14     B producer: the chunk's pre-split R limbs (core-matrix layout, one contiguous cp.async.bulk)
+//   warps 4-11  converters (thread = row, two sets alternating over the chunks): FP32 -> two FP16 limbs, K-major
+//               core-matrix A operand, per-chunk energies for the row's error bound
+//   warp 12     one thread issues 6 tcgen05.mma (M128 x NT x K16) per chunk and the commits
 //   warps 0-3   epilogue (thread = row = TMEM lane): accumulator -> registers -> rescale -> global
 // Bounds (C4: 1M x 300): HBM 8*d B/row = 2.4 GB -> 0.37 ms; tensor 6*d*d' flop/row (d' = padded width) = 0.26 ms.
 #include <cuda.h>
@@ -43,11 +44,12 @@ using namespace ptx;
 constexpr int kPT = 128;  // rows per tile (UMMA M)
 constexpr int kKC = 32;   // x columns per chunk (two K = 16 slices)
 constexpr int kXP = 36;   // floats per row of an x stage: 144 B, an odd multiple of 16 B -> conflict-free 128-bit reads
-constexpr int kXS = 3;    // x stages
+constexpr int kMaxXS = 8; // x stages: as many as fit (a TMA box of 128 short row segments has a long latency)
 constexpr int kAS = 3;    // A stages
-constexpr int kMaxBS = 6; // B stages (as many as fit)
-constexpr int kPThreads = 32 * 11;
-constexpr int kWarpConv0 = 4, kWarpMma = 8, kWarpXProd = 9, kWarpBProd = 10;
+constexpr int kMaxBS = 3; // B stages (one contiguous bulk copy each, L2 resident)
+constexpr int kPThreads = 32 * 15;
+// warps 0-3 epilogue, 4-11 converters (two sets alternating over the K chunks), then MMA issuer and the two producers
+constexpr int kWarpConv0 = 4, kWarpMma = 12, kWarpXProd = 13, kWarpBProd = 14;
 constexpr int X_STAGE = kPT * kXP * 4;        // 18 432 B
 constexpr int A_LIMB = (kKC / 8) * kPT * 16;  // 8 192 B: [4 core columns][128 rows][8 halves]
 constexpr int A_STAGE = 2 * A_LIMB;
@@ -63,7 +65,7 @@ struct ProjParams {
     float limb_coef;
     const float *sx_dev;  // optional device-side scale (else sx_host)
     float sx_host, sr;
-    int d, NT, n_groups, n_chunks, b_stages;
+    int d, NT, n_groups, n_chunks, b_stages, x_stages;
     long long n, n_units;
 };
 
@@ -74,15 +76,16 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B_STAGE = 128 * p.NT;
     unsigned char *sX = smem;
-    unsigned char *sA = sX + kXS * X_STAGE;
+    unsigned char *sA = sX + (size_t)p.x_stages * X_STAGE;
     unsigned char *sB = sA + kAS * A_STAGE;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.b_stages * B_STAGE);
-    uint64_t *x_full = bars, *x_empty = bars + 4, *a_full = bars + 8, *a_empty = bars + 12, *b_full = bars + 16,
-             *b_empty = bars + 24, *acc_full = bars + 32, *acc_empty = bars + 34;
+    uint64_t *x_full = bars, *x_empty = bars + 8, *a_full = bars + 16, *a_empty = bars + 20, *b_full = bars + 24,
+             *b_empty = bars + 28, *acc_full = bars + 32, *acc_empty = bars + 34;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 36);
+    float *sE = reinterpret_cast<float *>(bars + 40);  // [2][n_chunks][128] chunk energies (only with rowerr)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kXS; i++) {
+        for (int i = 0; i < p.x_stages; i++) {
             mbar_init(&x_full[i], 1);
             mbar_init(&x_empty[i], 4);
         }
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
                     mbar_arrive_expect_tx(&x_full[s], (uint32_t)X_STAGE);
                     // rows / columns outside the matrix arrive as zeros
                     tma_load_2d(sX + (size_t)s * X_STAGE, &tmap, c * kKC, (int)(t * kPT), &x_full[s]);
-                    if (++s == kXS) {
+                    if (++s == p.x_stages) {
                         s = 0;
                         ph ^= 1;
                     }
@@ -191,21 +194,26 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
         __syncwarp();
     } else if (warp >= kWarpConv0) {
         // ===================== converters (thread = row) =====================
-        const int row = (warp - kWarpConv0) * 32 + lane;
-        int xs = 0, as = 0;
-        uint32_t xph = 0, aph = 1;
-        for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        // Two sets of four warps take the chunks alternately (global chunk counter parity), so that one set's
+        // convert -> publish latency overlaps the other's; thread = row within a set.
+        const int set = (warp - kWarpConv0) >> 2;
+        const int row = ((warp - kWarpConv0) & 3) * 32 + lane;
+        int xs = set, as = set;
+        uint32_t xph = 0, aph = 1, it = 0, un = 0;
+        for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x, un++) {
             const long long t = u / p.n_groups;
             const int g = (int)(u % p.n_groups);
-            float ss = 0.f, eb = 0.f;
-            bool bad = false;
-            for (int c = 0; c < p.n_chunks; c++) {
+            const bool want_err = p.rowerr != nullptr && g == 0;
+            float *se = sE + (size_t)(un & 1) * p.n_chunks * kPT;
+            for (int c = 0; c < p.n_chunks; c++, it++) {
+                if ((int)(it & 1) != set) continue;
                 mbar_wait(&x_full[xs], xph);
                 const float4 *xr = reinterpret_cast<const float4 *>(sX + (size_t)xs * X_STAGE + (size_t)row * kXP * 4);
                 float4 v[kKC / 4];
 #pragma unroll
                 for (int i = 0; i < kKC / 4; i++) v[i] = xr[i];
                 uint32_t hw[kKC / 2], lw[kKC / 2];
+                float ss = 0.f, big = 0.f;
 #pragma unroll
                 for (int i = 0; i < kKC / 4; i++) {
                     const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
                         ss = fmaf(a0, a0, ss);
                         ss = fmaf(a1, a1, ss);
                         const float s0 = a0 * sx, s1 = a1 * sx;
-                        bad |= !(fabsf(s0) < kHalfLimit) | !(fabsf(s1) < kHalfLimit);  // also NaN / Inf
+                        big = fmaxf(big, fmaxf(fabsf(s0), fabsf(s1)));
                         const __half2 hh = __floats2half2_rn(s0, s1);
                         const float2 hf = __half22float2(hh);
                         const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
@@ -223,8 +231,8 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
                         lw[2 * i + h] = *reinterpret_cast<const uint32_t *>(&ll);
                     }
                 }
-                // every partial sum up to the end of this chunk is at most ||x[0..i)|| * ||r[0..i), j|| (Cauchy-Schwarz)
-                if (p.rowerr != nullptr) eb = fmaf(sqrtf(ss), __ldg(p.chunk_w + c), eb);
+                // chunk energy; NaN marks a chunk the split cannot represent (NaN / Inf make ss itself non-finite)
+                if (want_err) se[c * kPT + row] = (big < kHalfLimit && ss < 3.0e38f) ? ss : __int_as_float(0x7fc00000);
                 mbar_wait(&a_empty[as], aph);
                 unsigned char *a = sA + (size_t)as * A_STAGE;
 #pragma unroll
@@ -240,18 +248,32 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
                     mbar_arrive(&a_full[as]);
                     mbar_arrive(&x_empty[xs]);  // every lane has consumed its x values by now
                 }
-                if (++xs == kXS) {
-                    xs = 0;
+                xs += 2;
+                if (xs >= p.x_stages) {
+                    xs -= p.x_stages;
                     xph ^= 1;
                 }
-                if (++as == kAS) {
-                    as = 0;
+                as += 2;
+                if (as >= kAS) {
+                    as -= kAS;
                     aph ^= 1;
                 }
             }
-            const long long grow = t * kPT + row;
-            if (g == 0 && p.rowerr != nullptr && grow < p.n)
-                p.rowerr[grow] = bad ? __int_as_float(0x7fc00000) : fmaf(p.limb_coef, sqrtf(ss), eb) * 1.001f;
+            if (want_err) {
+                // both sets have written their chunk energies of this unit (the buffer alternates per unit, and a set
+                // cannot run more than one unit ahead of this barrier)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const long long grow = t * kPT + row;
+                if (set == 0 && grow < p.n) {
+                    // every partial sum over i < I is at most ||x[0..I)|| * max_j ||r[0..I), j|| (Cauchy-Schwarz)
+                    float ss = 0.f, eb = 0.f;
+                    for (int c = 0; c < p.n_chunks; c++) {
+                        ss += se[c * kPT + row];
+                        eb = fmaf(sqrtf(ss), __ldg(p.chunk_w + c), eb);
+                    }
+                    p.rowerr[grow] = fmaf(p.limb_coef, sqrtf(ss), eb) * 1.001f;  // NaN if any chunk was NaN
+                }
+            }
         }
     } else {
         // ===================== epilogue (thread = row = TMEM lane) =====================
@@ -470,6 +492,9 @@ bool project_tensor_call_supported(const ProjTensorOperands &ops, const float *x
     return true;
 }
 
+// the per-row error bound keeps two buffers of per-chunk energies in shared memory
+bool project_tensor_rowerr_supported(const ProjTensorOperands &ops) { return ops.ready() && ops.n_chunks <= 32; }
+
 rb_status launch_project_sample_scale(const float *x, size_t n, size_t d, ptrdiff_t ldx, float *scratch4, cudaStream_t stream)
 {
     // scratch4: [0] = sx (out), [1] = |x|max bits, [2] = block counter
@@ -512,16 +537,20 @@ rb_status launch_project_tensor(const ProjTensorOperands &ops, const float *x, s
     p.n_chunks = ops.n_chunks;
     p.n = (long long)n;
     p.n_units = (long long)ceil_div(n, (size_t)kPT) * ops.n_groups;
-    const size_t fixed = (size_t)kXS * X_STAGE + (size_t)kAS * A_STAGE + 40 * sizeof(uint64_t);
     const size_t b_stage = (size_t)128 * ops.NT;
-    int bs = (int)((kSmemLimit - fixed) / b_stage);
-    if (bs > kMaxBS) bs = kMaxBS;
-    if (bs < 2) {
-        set_error("project_tc: no room for the B ring (NT=%d)", ops.NT);
+    const size_t e_bytes = rowerr ? (size_t)2 * ops.n_chunks * kPT * sizeof(float) : 0;
+    const size_t fixed = (size_t)kAS * A_STAGE + 40 * sizeof(uint64_t) + e_bytes;
+    int bs = ops.NT > 192 ? 2 : kMaxBS;
+    int xs = fixed + (size_t)bs * b_stage < (size_t)kSmemLimit
+                 ? (int)((kSmemLimit - fixed - (size_t)bs * b_stage) / X_STAGE) : 0;
+    if (xs > kMaxXS) xs = kMaxXS;
+    if (xs < 2) {
+        set_error("project_tc: no room for the x ring (NT=%d, d=%d)", ops.NT, ops.d);
         return RB_ERR_UNSUPPORTED;
     }
     p.b_stages = bs;
-    const size_t smem = fixed + (size_t)bs * b_stage;
+    p.x_stages = xs;
+    const size_t smem = fixed + (size_t)xs * X_STAGE + (size_t)bs * b_stage;
     CUtensorMap tmap;
     RB_TRY(make_tensor_map(x, n, (size_t)ops.d, ldx, &tmap));
     RB_CUDA_TRY(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

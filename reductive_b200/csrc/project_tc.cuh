@@ -24,6 +24,8 @@ struct ProjTensorOperands {
 bool project_tensor_shape_supported(size_t d);
 bool project_tensor_call_supported(const ProjTensorOperands &ops, const float *x, size_t n, ptrdiff_t ldx, const float *y,
                                    ptrdiff_t ldy);
+// ... and whether the kernel can also produce the per-row error bound the encode needs (d <= 1024)
+bool project_tensor_rowerr_supported(const ProjTensorOperands &ops);
 // power-of-two scale for x from a known bound on |x|
 float project_scale_for_absmax(float amax);
 // ... or from a strided sample of rows, on the device: scratch4[0] receives the scale (scratch4 = 4 floats)
