@@ -419,17 +419,28 @@ ordered_chain_kernel(const float *__restrict__ x, long long ldx, int M, int k, i
     float sqf = 0.f;  // this lane's share of sum ||x||^2 in this chunk (<= a few hundred terms), widened once below
     int rem = (int)(e - s);
     const uint16_t *seg0 = list + ((size_t)m * n_chunks + chunk) * kChunkRows;  // always readable
-    while (__any_sync(0xffffffffu, rem > 0)) {
-        // loads are unconditional (indices clamped to the last valid row, finished chains re-read the segment start);
-        // only the adds are predicated
+    // Loads are unconditional (indices clamped to the last valid row, finished chains re-read the segment start); only
+    // the adds are predicated.  The row offsets of batch b + 1 are fetched while batch b's gathers are in flight, so a
+    // batch costs one memory round trip, not two.
+    unsigned off[UN];
+    {
         const uint16_t *spu = rem > 0 ? sp : seg0;
         const int last = max(min(rem, UN), 1) - 1;
-        unsigned off[UN];
-        float v[UN];
 #pragma unroll
         for (int u = 0; u < UN; u++) off[u] = (unsigned)__ldg(spu + min(u, last));
+    }
+    while (__any_sync(0xffffffffu, rem > 0)) {
+        float v[UN];
 #pragma unroll
         for (int u = 0; u < UN; u++) v[u] = ldg_l2_128(reinterpret_cast<const float *>(xc + (unsigned long long)off[u] * (unsigned long long)pitch_b));
+        sp += UN;
+        const int rem_next = rem - UN;
+        {
+            const uint16_t *spu = rem_next > 0 ? sp : seg0;
+            const int last = max(min(rem_next, UN), 1) - 1;
+#pragma unroll
+            for (int u = 0; u < UN; u++) off[u] = (unsigned)__ldg(spu + min(u, last));
+        }
 #pragma unroll
         for (int u = 0; u < UN; u++) {
             if (u < rem) {
@@ -437,8 +448,7 @@ ordered_chain_kernel(const float *__restrict__ x, long long ldx, int M, int k, i
                 sqf = fmaf(v[u], v[u], sqf);
             }
         }
-        sp += UN;
-        rem -= UN;
+        rem = rem_next;
     }
     sq = (double)sqf;
     if (on) {
