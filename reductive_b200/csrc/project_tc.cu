@@ -44,9 +44,10 @@ using namespace ptx;
 constexpr int kPT = 128;  // rows per tile (UMMA M)
 constexpr int kKC = 32;   // x columns per chunk (two K = 16 slices)
 constexpr int kXP = 36;   // floats per row of an x stage: 144 B, an odd multiple of 16 B -> conflict-free 128-bit reads
-constexpr int kMaxXS = 8; // x stages: as many as fit (a TMA box of 128 short row segments has a long latency)
+constexpr int kMaxXS = 8; // x stages
 constexpr int kAS = 3;    // A stages
-constexpr int kMaxBS = 3; // B stages (one contiguous bulk copy each, L2 resident)
+constexpr int kMaxBS = 4; // B stages: the R limbs are re-streamed from L2 for every unit, and the depth of this ring
+                          // (bytes in flight) is what the kernel's throughput follows (measured 3 -> 6 stages: +10 %)
 constexpr int kPThreads = 32 * 15;
 // warps 0-3 epilogue, 4-11 converters (two sets alternating over the K chunks), then MMA issuer and the two producers
 constexpr int kWarpConv0 = 4, kWarpMma = 12, kWarpXProd = 13, kWarpBProd = 14;
@@ -80,9 +81,9 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
     unsigned char *sB = sA + kAS * A_STAGE;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.b_stages * B_STAGE);
     uint64_t *x_full = bars, *x_empty = bars + 8, *a_full = bars + 16, *a_empty = bars + 20, *b_full = bars + 24,
-             *b_empty = bars + 28, *acc_full = bars + 32, *acc_empty = bars + 34;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 36);
-    float *sE = reinterpret_cast<float *>(bars + 40);  // [2][n_chunks][128] chunk energies (only with rowerr)
+             *b_empty = bars + 32, *acc_full = bars + 40, *acc_empty = bars + 42;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 44);
+    float *sE = reinterpret_cast<float *>(bars + 48);  // [2][n_chunks][128] chunk energies (only with rowerr)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.x_stages; i++) {
@@ -539,14 +540,23 @@ rb_status launch_project_tensor(const ProjTensorOperands &ops, const float *x, s
     p.n_units = (long long)ceil_div(n, (size_t)kPT) * ops.n_groups;
     const size_t b_stage = (size_t)128 * ops.NT;
     const size_t e_bytes = rowerr ? (size_t)2 * ops.n_chunks * kPT * sizeof(float) : 0;
-    const size_t fixed = (size_t)kAS * A_STAGE + 40 * sizeof(uint64_t) + e_bytes;
-    int bs = ops.NT > 192 ? 2 : kMaxBS;
-    int xs = fixed + (size_t)bs * b_stage < (size_t)kSmemLimit
-                 ? (int)((kSmemLimit - fixed - (size_t)bs * b_stage) / X_STAGE) : 0;
-    if (xs > kMaxXS) xs = kMaxXS;
-    if (xs < 2) {
-        set_error("project_tc: no room for the x ring (NT=%d, d=%d)", ops.NT, ops.d);
+    const size_t fixed = (size_t)kAS * A_STAGE + 48 * sizeof(uint64_t) + e_bytes;
+    // three x stages, then as many B stages as fit (up to 8), then the rest to x
+    static const int env_xs = getenv("RB_PROJ_XS") ? atoi(getenv("RB_PROJ_XS")) : 3;
+    int xs = env_xs;
+    int bs = fixed + (size_t)xs * X_STAGE < (size_t)kSmemLimit ? (int)((kSmemLimit - fixed - (size_t)xs * X_STAGE) / b_stage) : 0;
+    if (bs > 8) bs = 8;
+    if (bs < 2) {
+        xs = 2;
+        bs = fixed + (size_t)xs * X_STAGE < (size_t)kSmemLimit ? (int)((kSmemLimit - fixed - (size_t)xs * X_STAGE) / b_stage) : 0;
+    }
+    if (bs < 2) {
+        set_error("project_tc: no room for the operand rings (NT=%d, d=%d)", ops.NT, ops.d);
         return RB_ERR_UNSUPPORTED;
+    }
+    {
+        const int more = (int)((kSmemLimit - fixed - (size_t)bs * b_stage) / X_STAGE);
+        xs = more > kMaxXS ? kMaxXS : more;
     }
     p.b_stages = bs;
     p.x_stages = xs;
