@@ -261,6 +261,38 @@ def test_projected_encode_decode(oracle, algo, palgo, n, M, k, dsub):
     assert np.abs(rec - want_rec).max() <= 1e-5 * np.abs(want_rec).max()
 
 
+@pytest.mark.parametrize("M,k,dsub,xscale", [(30, 256, 10, 1.0), (16, 256, 8, 1e-4), (12, 200, 16, 300.0)])
+def test_rotated_tensor_encode_adversarial(oracle, M, k, dsub, xscale):
+    """Tensor rotation + tensor encode on inputs built to break the certificate: rows that rotate onto (or a few ulp
+    off) centroid bisectors and onto exact centroids, NaN / Inf / huge / tiny / zero rows, a row far above the sampled
+    operand scale, duplicate centroids, a non-orthonormal R.  Codes must equal the oracle's bit for bit."""
+    d = M * dsub
+    q = random_codebook(M, k, dsub, 71)
+    q[:, 9] = q[:, 4]
+    rng = np.random.default_rng(72)
+    r = (orthonormal(d, 73) * rng.uniform(0.7, 1.5, size=(1, d))).astype(F)
+    y = near_tie_rows(q, 6_000, 74).astype(np.float64)      # wanted rotated rows ...
+    x_tie = np.linalg.solve(r.astype(np.float64).T, y.T).T.astype(F)   # ... and rows that rotate (almost) onto them
+    x = np.concatenate([x_tie, (normal((4_000, d), 75) * xscale).astype(F)])
+    x[10, 3] = np.nan
+    x[11, 7] = np.inf
+    x[12, :] = -np.inf
+    x[13, :] = 1e30
+    x[14, :] = 1e-30
+    x[15, :] = 0.0
+    x[16, :] = 1e-41
+    x[17, :] *= 1e6                                          # far above the sampled operand scale
+    x[18, 5] = 3e38
+    rb.set_project_algo(rb.PROJECT_TENSOR)
+    rb.set_encode_algo(rb.ENCODE_AUTO)
+    try:
+        codes = rb.Pq(r, q).quantize_batch(x, np.uint8)
+    finally:
+        rb.set_project_algo(rb.PROJECT_AUTO)
+    want = oracle.quantize_batch(q, r, x, np.uint8, n_threads=8)
+    assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ in rows {np.unique(np.nonzero(codes != want)[0])[:10]}"
+
+
 @pytest.mark.parametrize("d,scale", [(300, 1.0), (768, 1e-3), (128, 37.0), (36, 1e4), (260, 1.0)])
 def test_tensor_rotation_decode_error(d, scale):
     """The tcgen05 rotation against float64: error inside north_star's 1e-5 of the largest output, for codebooks of very
