@@ -22,7 +22,8 @@
 //   warps 4-11  converters (thread = row, two sets alternating over the chunks): FP32 -> two FP16 limbs, K-major
 //               core-matrix A operand, per-chunk energies for the row's error bound
 //   warp 12     one thread issues 6 tcgen05.mma (M128 x NT x K16) per chunk and the commits
-//   warps 0-3   epilogue (thread = row = TMEM lane): accumulator -> registers -> rescale -> global
+//   warps 0-3   epilogue (thread = row = TMEM lane): accumulator -> registers -> rescale -> swizzled staging tile in
+//               shared memory -> TMA tensor store (32 columns x 128 rows per store)
 // Bounds (C4: 1M x 300): HBM 8*d B/row = 2.4 GB -> 0.37 ms; tensor 6*d*d' flop/row (d' = padded width) = 0.26 ms.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -54,6 +55,7 @@ constexpr int kWarpConv0 = 4, kWarpMma = 12, kWarpXProd = 13, kWarpBProd = 14;
 constexpr int X_STAGE = kPT * kXP * 4;        // 18 432 B
 constexpr int A_LIMB = (kKC / 8) * kPT * 16;  // 8 192 B: [4 core columns][128 rows][8 halves]
 constexpr int A_STAGE = 2 * A_LIMB;
+constexpr int Y_STAGE = kPT * 128;            // 16 384 B: 128 rows x 32 floats, 128-byte swizzled (TMA store source)
 constexpr int kSmemLimit = 227 * 1024;
 constexpr float kHalfLimit = 32768.f;  // |x * sx| must stay below this for the FP16 split
 
@@ -71,12 +73,15 @@ struct ProjParams {
 };
 
 __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_constant__ ProjParams p,
-                                                                  const __grid_constant__ CUtensorMap tmap)
+                                                                  const __grid_constant__ CUtensorMap tmap,
+                                                                  const __grid_constant__ CUtensorMap ymap)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B_STAGE = 128 * p.NT;
-    unsigned char *sX = smem;
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();  // the swizzle pattern below assumes this alignment
+    unsigned char *sY = smem;  // two output staging tiles, 1 024-byte aligned for the 128-byte swizzle
+    unsigned char *sX = sY + 2 * Y_STAGE;
     unsigned char *sA = sX + (size_t)p.x_stages * X_STAGE;
     unsigned char *sB = sA + kAS * A_STAGE;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.b_stages * B_STAGE);
@@ -278,38 +283,43 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
         }
     } else {
         // ===================== epilogue (thread = row = TMEM lane) =====================
+        // accumulator -> registers -> rescale -> swizzled staging tile -> TMA store.  (Storing from registers, one
+        // 16-byte piece per lane and row, cost 32 store wavefronts per instruction and a third of the kernel.)
         const int row = warp * 32 + lane;
         const float inv = 1.0f / (sx * p.sr);  // a power of two
-        uint32_t un = 0;
+        uint32_t un = 0, blk = 0;
         for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x, un++) {
             const long long t = u / p.n_groups;
             const int g = (int)(u % p.n_groups);
             const uint32_t buf = un & 1;
-            const long long grow = t * kPT + row;
             mbar_wait(&acc_full[buf], (un >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256;
-            const int col_end = min(p.d, (g + 1) * p.NT);
-            float *yr = p.y + grow * p.ldy;
-            for (int c0 = 0; c0 < p.NT; c0 += 32) {
+            for (int c0 = 0; c0 < p.NT && g * p.NT + c0 < p.d; c0 += 32, blk++) {
+                unsigned char *yb = sY + (size_t)(blk & 1) * Y_STAGE;
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
+                // the store issued two blocks ago has finished reading this staging tile
+                if (threadIdx.x == 0) bulk_wait_group_read<1>();
+                asm volatile("bar.sync 2, 128;" ::: "memory");
                 tmem_wait_ld(v);
-                if (grow < p.n) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int col = g * p.NT + c0 + 4 * i;
-                        if (col < col_end)  // d % 4 == 0: a 16-byte piece is inside or outside as a whole
-                            __stcs(reinterpret_cast<float4 *>(yr + col),
-                                   make_float4(__uint_as_float(v[4 * i]) * inv, __uint_as_float(v[4 * i + 1]) * inv,
-                                               __uint_as_float(v[4 * i + 2]) * inv, __uint_as_float(v[4 * i + 3]) * inv));
-                    }
+                for (int i = 0; i < 8; i++)
+                    *reinterpret_cast<float4 *>(yb + (size_t)row * 128 + (size_t)((i ^ (row & 7)) * 16)) =
+                        make_float4(__uint_as_float(v[4 * i]) * inv, __uint_as_float(v[4 * i + 1]) * inv,
+                                    __uint_as_float(v[4 * i + 2]) * inv, __uint_as_float(v[4 * i + 3]) * inv);
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (threadIdx.x == 0) {
+                    tma_store_2d(&ymap, g * p.NT + c0, (int)(t * kPT), yb);  // rows >= n / columns >= d are clipped
+                    bulk_commit_group();
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        if (threadIdx.x == 0) bulk_wait_group_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -372,7 +382,8 @@ __global__ void proj_sample_scale_kernel(const float *__restrict__ x, long long 
     }
 }
 
-rb_status make_tensor_map(const float *x, size_t n, size_t d, ptrdiff_t ldx, CUtensorMap *out)
+rb_status make_tensor_map(const float *x, size_t n, size_t d, ptrdiff_t ldx, CUtensorMap *out, unsigned box_cols = kXP,
+                          bool swizzle128 = false)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -391,11 +402,11 @@ rb_status make_tensor_map(const float *x, size_t n, size_t d, ptrdiff_t ldx, CUt
     }
     const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n};
     const cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kXP, (cuuint32_t)kPT};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kPT};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%zu d=%zu ldx=%td)", (int)r, n, d, ldx);
         return RB_ERR_CUDA;
@@ -439,7 +450,7 @@ rb_status ProjTensorOperands::prepare(const float *r_dev, const float *r_host, s
     rcolmax = (float)(std::sqrt(colmax2) * (1.0 + 1e-6));
     const int dp16 = (d + 15) / 16 * 16;
     n_groups = (dp16 + 255) / 256;
-    NT = ((dp16 + n_groups - 1) / n_groups + 15) / 16 * 16;
+    NT = ((dp16 + n_groups - 1) / n_groups + 31) / 32 * 32;  // whole 32-column output blocks per group
     n_chunks = (d + kKC - 1) / kKC;
     bytes = (size_t)n_groups * n_chunks * 128 * NT;
     // Error model of y~_j against the reference's FP32 y_j (encode only).  Per K chunk of 32:
@@ -540,7 +551,7 @@ rb_status launch_project_tensor(const ProjTensorOperands &ops, const float *x, s
     p.n_units = (long long)ceil_div(n, (size_t)kPT) * ops.n_groups;
     const size_t b_stage = (size_t)128 * ops.NT;
     const size_t e_bytes = rowerr ? (size_t)2 * ops.n_chunks * kPT * sizeof(float) : 0;
-    const size_t fixed = (size_t)kAS * A_STAGE + 48 * sizeof(uint64_t) + e_bytes;
+    const size_t fixed = (size_t)2 * Y_STAGE + (size_t)kAS * A_STAGE + 48 * sizeof(uint64_t) + e_bytes;
     // three x stages, then as many B stages as fit (up to 8), then the rest to x
     static const int env_xs = getenv("RB_PROJ_XS") ? atoi(getenv("RB_PROJ_XS")) : 3;
     int xs = env_xs;
@@ -561,8 +572,9 @@ rb_status launch_project_tensor(const ProjTensorOperands &ops, const float *x, s
     p.b_stages = bs;
     p.x_stages = xs;
     const size_t smem = fixed + (size_t)xs * X_STAGE + (size_t)bs * b_stage;
-    CUtensorMap tmap;
+    CUtensorMap tmap, ymap;
     RB_TRY(make_tensor_map(x, n, (size_t)ops.d, ldx, &tmap));
+    RB_TRY(make_tensor_map(y, n, (size_t)ops.d, ldy, &ymap, 32, true));
     RB_CUDA_TRY(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -571,7 +583,7 @@ rb_status launch_project_tensor(const ProjTensorOperands &ops, const float *x, s
     grid -= grid % ops.n_groups;
     if (grid < ops.n_groups) grid = ops.n_groups;
     if (grid > p.n_units) grid = p.n_units;
-    project_tc_kernel<<<(unsigned)grid, kPThreads, smem, stream>>>(p, tmap);
+    project_tc_kernel<<<(unsigned)grid, kPThreads, smem, stream>>>(p, tmap, ymap);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }

@@ -87,6 +87,20 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, in
                  "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
 }
+// 2-D TMA tile store shared -> global (bulk async-group completion); elements outside the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int c0, int c1, const void *src_smem)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0),
+                 "r"(c1), "r"(smem_u32(src_smem))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const void *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
