@@ -17,7 +17,7 @@
 //
 // Work split: unit = (128-row tile, group of NT <= 256 output columns); persistent CTAs walk the units with the
 // groups of one tile adjacent, so x is read from HBM once.  Per unit the K loop runs over chunks of 32 x-columns:
-//   warp 13     x producer: one TMA tensor-map box (128 rows x 36 floats, pitch an odd multiple of 16 B) per chunk
+//   warp 13     x producer: one TMA tensor-map box (128 rows x 32 floats, 128-byte swizzle) per chunk
 //   warp 14     B producer: the chunk's pre-split R limbs (core-matrix layout, one contiguous cp.async.bulk)
 //   warps 4-11  converters (thread = row, two sets alternating over the chunks): FP32 -> two FP16 limbs, K-major
 //               core-matrix A operand, per-chunk energies for the row's error bound
@@ -44,15 +44,16 @@ using namespace ptx;
 
 constexpr int kPT = 128;  // rows per tile (UMMA M)
 constexpr int kKC = 32;   // x columns per chunk (two K = 16 slices)
-constexpr int kXP = 36;   // floats per row of an x stage: 144 B, an odd multiple of 16 B -> conflict-free 128-bit reads
-constexpr int kMaxXS = 8; // x stages
-constexpr int kAS = 3;    // A stages
+constexpr int kXP = 32;   // floats per row of an x stage: 128 B, loaded with the 128-byte TMA swizzle -> the 16-byte chunk
+                          // i of row r sits at chunk i ^ (r & 7), so the row-per-thread 128-bit reads are conflict free
+constexpr int kMaxXS = 8; // x stages (an even number: see the converters)
+constexpr int kAS = 2;    // A stages, one per converter set
 constexpr int kMaxBS = 4; // B stages: the R limbs are re-streamed from L2 for every unit, and the depth of this ring
                           // (bytes in flight) is what the kernel's throughput follows (measured 3 -> 6 stages: +10 %)
 constexpr int kPThreads = 32 * 15;
 // warps 0-3 epilogue, 4-11 converters (two sets alternating over the K chunks), then MMA issuer and the two producers
 constexpr int kWarpConv0 = 4, kWarpMma = 12, kWarpXProd = 13, kWarpBProd = 14;
-constexpr int X_STAGE = kPT * kXP * 4;        // 18 432 B
+constexpr int X_STAGE = kPT * kXP * 4;        // 16 384 B
 constexpr int A_LIMB = (kKC / 8) * kPT * 16;  // 8 192 B: [4 core columns][128 rows][8 halves]
 constexpr int A_STAGE = 2 * A_LIMB;
 constexpr int Y_STAGE = kPT * 128;            // 16 384 B: 128 rows x 32 floats, 128-byte swizzled (TMA store source)
@@ -201,7 +202,9 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
     } else if (warp >= kWarpConv0) {
         // ===================== converters (thread = row) =====================
         // Two sets of four warps take the chunks alternately (global chunk counter parity), so that one set's
-        // convert -> publish latency overlaps the other's; thread = row within a set.
+        // convert -> publish latency overlaps the other's; thread = row within a set.  The numbers of x and A stages
+        // are even, so a set always meets the same stages and sees EVERY phase of their barriers — a waiter that
+        // skips a phase of an mbarrier cannot tell "two phases later" from "not yet".
         const int set = (warp - kWarpConv0) >> 2;
         const int row = ((warp - kWarpConv0) & 3) * 32 + lane;
         int xs = set, as = set;
@@ -214,10 +217,10 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
             for (int c = 0; c < p.n_chunks; c++, it++) {
                 if ((int)(it & 1) != set) continue;
                 mbar_wait(&x_full[xs], xph);
-                const float4 *xr = reinterpret_cast<const float4 *>(sX + (size_t)xs * X_STAGE + (size_t)row * kXP * 4);
+                const unsigned char *xr = sX + (size_t)xs * X_STAGE + (size_t)row * kXP * 4;
                 float4 v[kKC / 4];
 #pragma unroll
-                for (int i = 0; i < kKC / 4; i++) v[i] = xr[i];
+                for (int i = 0; i < kKC / 4; i++) v[i] = *reinterpret_cast<const float4 *>(xr + ((i ^ (row & 7)) * 16));
                 uint32_t hw[kKC / 2], lw[kKC / 2];
                 float ss = 0.f, big = 0.f;
 #pragma unroll
@@ -552,28 +555,32 @@ rb_status launch_project_tensor(const ProjTensorOperands &ops, const float *x, s
     const size_t b_stage = (size_t)128 * ops.NT;
     const size_t e_bytes = rowerr ? (size_t)2 * ops.n_chunks * kPT * sizeof(float) : 0;
     const size_t fixed = (size_t)2 * Y_STAGE + (size_t)kAS * A_STAGE + 48 * sizeof(uint64_t) + e_bytes;
-    // three x stages, then as many B stages as fit (up to 8), then the rest to x
-    static const int env_xs = getenv("RB_PROJ_XS") ? atoi(getenv("RB_PROJ_XS")) : 3;
-    int xs = env_xs;
-    int bs = fixed + (size_t)xs * X_STAGE < (size_t)kSmemLimit ? (int)((kSmemLimit - fixed - (size_t)xs * X_STAGE) / b_stage) : 0;
-    if (bs > 8) bs = 8;
+    // four x stages (an even number, see the converters), then as many B stages as fit, then the rest to x
+    int xs = 4;
+    auto b_fit = [&](int xstages) {
+        const size_t used = fixed + (size_t)xstages * X_STAGE;
+        return used < (size_t)kSmemLimit ? (int)((kSmemLimit - used) / b_stage) : 0;
+    };
+    int bs = b_fit(xs);
     if (bs < 2) {
         xs = 2;
-        bs = fixed + (size_t)xs * X_STAGE < (size_t)kSmemLimit ? (int)((kSmemLimit - fixed - (size_t)xs * X_STAGE) / b_stage) : 0;
+        bs = b_fit(xs);
     }
     if (bs < 2) {
         set_error("project_tc: no room for the operand rings (NT=%d, d=%d)", ops.NT, ops.d);
         return RB_ERR_UNSUPPORTED;
     }
+    if (bs > 8) bs = 8;
     {
-        const int more = (int)((kSmemLimit - fixed - (size_t)bs * b_stage) / X_STAGE);
+        int more = (int)((kSmemLimit - fixed - (size_t)bs * b_stage) / X_STAGE);
+        more -= more % 2;
         xs = more > kMaxXS ? kMaxXS : more;
     }
     p.b_stages = bs;
     p.x_stages = xs;
     const size_t smem = fixed + (size_t)xs * X_STAGE + (size_t)bs * b_stage;
     CUtensorMap tmap, ymap;
-    RB_TRY(make_tensor_map(x, n, (size_t)ops.d, ldx, &tmap));
+    RB_TRY(make_tensor_map(x, n, (size_t)ops.d, ldx, &tmap, kXP, true));
     RB_TRY(make_tensor_map(y, n, (size_t)ops.d, ldy, &ymap, 32, true));
     RB_CUDA_TRY(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
