@@ -300,35 +300,43 @@ rotated_recheck_kernel(const uint32_t *__restrict__ counts, const uint32_t *__re
             row[q] = rows[(size_t)m * (size_t)n_cap + (live[q] ? idx : base)];  // base < cnt: a valid slot
             xr[q] = x0 + row[q] * ldx0;
         }
-        float rx[RPT][DSUB];
-        for (int i0 = 0; i0 < d; i0 += 256) {
-            float acc[RPT][DSUB];
+        // One pass over the row in steps of four components (d % 4 == 0, 16-byte aligned rows:
+        // project_tensor_call_supported), the next step's values already in flight; at every K block boundary of 256
+        // the block's chain is folded into the running result by a plain add (first block: assignment).
+        float rx[RPT][DSUB], acc[RPT][DSUB];
+        float4 nxt[RPT];
 #pragma unroll
-            for (int q = 0; q < RPT; q++)
+        for (int q = 0; q < RPT; q++) {
+            nxt[q] = __ldg(reinterpret_cast<const float4 *>(xr[q]));
 #pragma unroll
-                for (int t = 0; t < DSUB; t++) acc[q][t] = 0.f;
-            const int i1 = min(d, i0 + 256);
-            for (int i = i0; i < i1; i += 4) {  // d % 4 == 0, 16-byte aligned rows (project_tensor_call_supported)
-                float xe[RPT][4];
+            for (int t = 0; t < DSUB; t++) acc[q][t] = rx[q][t] = 0.f;
+        }
+        for (int i = 0; i < d; i += 4) {
+            float xe[RPT][4];
 #pragma unroll
-                for (int q = 0; q < RPT; q++) {
-                    const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr[q] + i));
-                    xe[q][0] = xv.x; xe[q][1] = xv.y; xe[q][2] = xv.z; xe[q][3] = xv.w;
-                }
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    float c[DSUB];
-                    load_centroid<DSUB>(rs + (size_t)(i + e) * DSUB, c);
-#pragma unroll
-                    for (int q = 0; q < RPT; q++)
-#pragma unroll
-                        for (int t = 0; t < DSUB; t++) acc[q][t] = __fmaf_rn(xe[q][e], c[t], acc[q][t]);
-                }
+            for (int q = 0; q < RPT; q++) {
+                xe[q][0] = nxt[q].x; xe[q][1] = nxt[q].y; xe[q][2] = nxt[q].z; xe[q][3] = nxt[q].w;
+                nxt[q] = __ldg(reinterpret_cast<const float4 *>(xr[q] + min(i + 4, d - 4)));
             }
 #pragma unroll
-            for (int q = 0; q < RPT; q++)
+            for (int e = 0; e < 4; e++) {
+                float c[DSUB];
+                load_centroid<DSUB>(rs + (size_t)(i + e) * DSUB, c);
 #pragma unroll
-                for (int t = 0; t < DSUB; t++) rx[q][t] = i0 == 0 ? acc[q][t] : __fadd_rn(rx[q][t], acc[q][t]);
+                for (int q = 0; q < RPT; q++)
+#pragma unroll
+                    for (int t = 0; t < DSUB; t++) acc[q][t] = __fmaf_rn(xe[q][e], c[t], acc[q][t]);
+            }
+            if (((i + 4) & 255) == 0 || i + 4 >= d) {
+                const bool first = i < 256;
+#pragma unroll
+                for (int q = 0; q < RPT; q++)
+#pragma unroll
+                    for (int t = 0; t < DSUB; t++) {
+                        rx[q][t] = first ? acc[q][t] : __fadd_rn(rx[q][t], acc[q][t]);
+                        acc[q][t] = 0.f;
+                    }
+            }
         }
         float xs[RPT], best[RPT];
         int bidx[RPT];

@@ -293,6 +293,32 @@ def test_rotated_tensor_encode_adversarial(oracle, M, k, dsub, xscale):
     assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ in rows {np.unique(np.nonzero(codes != want)[0])[:10]}"
 
 
+@pytest.mark.parametrize("n,M,dsub", [(400_000, 16, 8), (150_000, 30, 10)])
+def test_tensor_rotation_many_units_per_cta(n, M, dsub):
+    """Long runs of (tile, column group) units per CTA: the operand rings wrap many times (a converter set that skipped
+    barrier phases once read a stage early here).  Tensor rotation against the exact GPU GEMM on the same codes."""
+    import torch
+
+    k, d = 256, M * dsub
+    q = random_codebook(M, k, dsub, 81)
+    pq = rb.Pq(orthonormal(d, 82), q)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(83)
+    codes = torch.randint(0, k, (n, M), generator=g, device="cuda", dtype=torch.uint8)
+    rec_e = torch.empty((n, d), device="cuda")
+    rec_t = torch.empty((n, d), device="cuda")
+    try:
+        rb.set_project_algo(rb.PROJECT_EXACT)
+        pq.reconstruct_batch_into(codes, rec_e)
+        rb.set_project_algo(rb.PROJECT_TENSOR)
+        for _ in range(3):
+            pq.reconstruct_batch_into(codes, rec_t)
+    finally:
+        rb.set_project_algo(rb.PROJECT_AUTO)
+    torch.cuda.synchronize()
+    assert float((rec_e - rec_t).abs().max()) <= 1e-5 * float(rec_e.abs().max())
+
+
 @pytest.mark.parametrize("d,scale", [(300, 1.0), (768, 1e-3), (128, 37.0), (36, 1e4), (260, 1.0)])
 def test_tensor_rotation_decode_error(d, scale):
     """The tcgen05 rotation against float64: error inside north_star's 1e-5 of the largest output, for codebooks of very
