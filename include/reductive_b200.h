@@ -110,7 +110,9 @@ rb_status rb_pq_projection(const rb_pq *pq, float *out_host);     /* Pq::project
 /* ---- QuantizeVector (src/pq/traits.rs:75-99; impl pq.rs:252-303) ------------------------------ */
 
 /* quantize_batch_into  pq.rs:268-283 -> primitives.rs:64-104.  x [n, d] f32, codes [n, M].
- * No check that k-1 fits code_width (the reference's batch path truncates, primitives.rs:100). */
+ * No check that k-1 fits code_width (the reference's batch path truncates, primitives.rs:100).
+ * A quantizer with a projection rotates the rows first (pq.rs:276) with the kernel rb_set_project_algo selects;
+ * the codes are the same under every choice. */
 rb_status rb_pq_quantize_batch(const rb_pq *pq, const float *x, size_t n, ptrdiff_t x_row_stride,
                                ptrdiff_t x_col_stride, void *codes, int code_width,
                                ptrdiff_t code_row_stride, ptrdiff_t code_col_stride,
