@@ -146,10 +146,10 @@ static rb_status encode_device(const DeviceCodebook &cb, const TensorOperands *t
     return launch_encode_exact(cb, x, n, ldx, codes, code_width, crs, ccs, seq_norm, stream);
 }
 
-// rows per workspace chunk so that a [rows, d] f32 temporary stays around 1 GiB
+// rows per workspace chunk so that a [rows, d] f32 temporary stays around 2 GiB
 static size_t workspace_rows(size_t n, size_t d)
 {
-    size_t rows = ((size_t)1 << 30) / (d * sizeof(float));
+    size_t rows = ((size_t)2 << 30) / (d * sizeof(float));
     if (rows < 1024) rows = 1024;
     return rows < n ? rows : n;
 }

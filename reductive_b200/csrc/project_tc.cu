@@ -516,7 +516,7 @@ rb_status launch_project_sample_scale(const float *x, size_t n, size_t d, ptrdif
     RB_CUDA_TRY(cudaMemsetAsync(scratch4, 0, 4 * sizeof(float), stream));
     const long long sample_rows = 2048;
     const long long row_step = n > (size_t)sample_rows ? (long long)(n / sample_rows) : 1;
-    const unsigned blocks = 64;
+    const unsigned blocks = 512;  // four sampled rows per block: the reads of a block are one round trip deep
     proj_sample_scale_kernel<<<blocks, 128, 0, stream>>>(x, (long long)n, (int)d, (long long)ldx, row_step,
                                                          reinterpret_cast<unsigned *>(scratch4 + 1), scratch4,
                                                          reinterpret_cast<unsigned *>(scratch4 + 2), blocks);
