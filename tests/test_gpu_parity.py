@@ -243,7 +243,8 @@ def palgo(request):
     rb.set_project_algo(rb.PROJECT_AUTO)
 
 
-@pytest.mark.parametrize("n,M,k,dsub", [(6_000, 10, 256, 30), (6_000, 30, 256, 10), (1_000, 4, 32, 80)])
+@pytest.mark.parametrize("n,M,k,dsub", [(6_000, 10, 256, 30), (6_000, 30, 256, 10), (1_000, 4, 32, 80),
+                                        (3_000, 96, 256, 8), (5_000, 16, 128, 8)])
 def test_projected_encode_decode(oracle, algo, palgo, n, M, k, dsub):
     """Opq / GaussianOpq use: x.R before the argmin, R^T after the gather (pq.rs:276, 323-326).  d = 300/320 > kc
     exercises the 256-block split of the reference GEMM.  Codes are bit-exact under every rotation kernel; the
