@@ -235,7 +235,9 @@ __device__ __forceinline__ float min16(const uint32_t *v)
 #define RB_PH_END() do { } while (0)
 #endif
 
-template <int DSUB>
+// ROT: x is an approximate rotation (EncParams::rowerr); a separate instantiation so that the plain kernel carries
+// none of its code (the run-time branch cost 3 % on C2)
+template <int DSUB, bool ROT>
 __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_constant__ EncParams p,
                                                                 const __grid_constant__ CUtensorMap tmap)
 {
@@ -250,7 +252,9 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
     unsigned char *sX = sB + (size_t)p.gm * B_BYTES;
     unsigned char *sA = sX + (size_t)kXStages * xs_bytes;
     float *sMarg = reinterpret_cast<float *>(sA + (size_t)p.a_stages * A_BYTES);  // [kMargRing][kTile]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sMarg + kMargRing * kTile);
+    // rotated input: two more per-row values (margin = sMarg + sMargB * sqrt(max(sMargC + min score, 0)), see below)
+    float *sMargB = sMarg + kMargRing * kTile, *sMargC = sMargB + kMargRing * kTile;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sMarg + (ROT ? 3 : 1) * kMargRing * kTile);
     uint64_t *x_full = bars, *x_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 8, *acc_full = bars + 12,
              *acc_empty = bars + 14, *b_full = bars + 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
             RB_PH(1);
             const float4 *xr = reinterpret_cast<const float4 *>(sX + (size_t)stage * xs_bytes + (size_t)row * p.pitch_f * 4);
             float perr = 0.f;  // bound on the error of each component of this row (0: the row is exact)
-            if (p.rowerr != nullptr) {
+            if constexpr (ROT) {
                 const long long grow = t * kTile + row;
                 perr = (grow < p.n ? p.rowerr[grow] : 0.f) + p.perr_floor / p.perr_sx[0];
             }
@@ -416,11 +420,24 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     const float xs_sc = xs * scale2;
                     const bool bad = cb_bad || !(xs_sc < p.xs_limit);
                     const float csmax = p.consts[g * p.gm + ml0 + h];
-                    // a component error of perr moves a score 2 x.c by at most 2 sqrt(dsub) perr ||c||; margin = 2 x bound
-                    float marg = margin_of(xs, csmax, DSUB);
-                    if (p.rowerr != nullptr) marg += 4.0f * perr * sqrtf((float)DSUB * csmax);
-                    marg *= scale2;
-                    if (bad || !(marg < 3.0e38f)) marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
+                    float marg = margin_of(xs, csmax, DSUB) * scale2;
+                    float margb = 0.f, margc = 0.f;
+                    if constexpr (ROT) {
+                        // Rotated input: the subvector is off by delta, ||delta|| <= sqrt(dsub) * perr, which moves the
+                        // DIFFERENCE of two scores by 2 delta.(c_j - c_i) <= 2 ||delta|| (a + b), a and b the true
+                        // distances to the two centroids.  A centroid with b - a > 4 ||delta|| + 2 sqrt(e) (e = half the
+                        // base margin) is ranked correctly by the reference whatever we measure, since then
+                        // b^2 - a^2 >= (b - a)^2 > 4 e; for the others a + b <= 2 a + 4 ||delta|| + 2 sqrt(e), so
+                        //   margin = base + 4 ||delta|| (a + 3 ||delta|| + sqrt(e)),  a <= sqrt(d~_min + e) + ||delta||
+                        // with d~_min = xs + (minimum score), known only in the epilogue.  All in scaled units.
+                        const float ds = sqrtf((float)DSUB) * perr * scale * 1.02f;
+                        const float eb = 0.5f * marg;
+                        marg += 4.0f * ds * (4.0f * ds + sqrtf(eb));
+                        margb = 4.0f * ds;
+                        margc = xs_sc + eb;
+                    }
+                    if (bad || !(marg < 3.0e38f) || !(margb < 3.0e38f))
+                        marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
                     RB_PH(2);
                     mbar_wait(&a_empty[as], aph ^ 1);
                     RB_PH(3);
@@ -430,6 +447,10 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                         *reinterpret_cast<uint4 *>(a + ((size_t)c8 * kTile + row) * 16) =
                             make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
                     sMarg[(u % kMargRing) * kTile + row] = marg;
+                    if constexpr (ROT) {
+                        sMargB[(u % kMargRing) * kTile + row] = margb;
+                        sMargC[(u % kMargRing) * kTile + row] = margc;
+                    }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[as]);
@@ -493,7 +514,12 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[set]);
                 RB_PH(2);
-                const float marg = sMarg[(u % kMargRing) * kTile + row];
+                float marg = sMarg[(u % kMargRing) * kTile + row];
+                float margb = 0.f, margc = 0.f;
+                if constexpr (ROT) {
+                    margb = sMargB[(u % kMargRing) * kTile + row];
+                    margc = sMargC[(u % kMargRing) * kTile + row];
+                }
 
                 // minimum of the 16 block minima as a tree (short dependency chain)
                 const float ma = fmin3(B[0], B[1], B[2]), mb = fmin3(B[3], B[4], B[5]), mc = fmin3(B[6], B[7], B[8]);
@@ -503,6 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                 // exactly 1 for v < thr and exactly 0 for v >= thr or NaN as long as |thr| >= 2^-14 (then thr - v
                 // is zero or at least ulp(thr) >= 2^-37).  acc = sum t_i * (64 + i) lies in [64, 80) iff exactly
                 // one t_i is set, and then names it.  Four partial sums each keep the dependency chains short.
+                if constexpr (ROT) marg = fmaf(margb, sqrtf(fmaxf(margc + m1, 0.f)), marg);
                 const float thr = m1 + marg;
                 const float SC = 1.099511627776e12f;  // 2^40
                 const float thr_sc = thr * SC;
@@ -560,15 +587,15 @@ struct Plan {
 // Column grouping and CTA allocation.  A CTA keeps the B operands of one group of gm subquantizers in shared
 // memory for its whole life and walks 128-row tiles; groups get CTAs in proportion to their width.  Chosen to
 // minimise the busiest CTA's number of (tile, subquantizer) units.
-Plan make_plan_uncached(size_t M, size_t dsub, size_t n_tiles, int sms);
+Plan make_plan_uncached(size_t M, size_t dsub, size_t n_tiles, int sms, int marg_rings);
 
 // The search below costs 40-250 us of host time (it is quadratic in the number of column groups), which shows in
 // loops of short calls (k-means on small row counts): the last few shapes are remembered.
-Plan make_plan(size_t M, size_t dsub, size_t n_tiles, int sms)
+Plan make_plan(size_t M, size_t dsub, size_t n_tiles, int sms, int marg_rings = 1)
 {
     struct Entry {
         size_t M, dsub, n_tiles;
-        int sms;
+        int sms, marg_rings;
         Plan plan;
     };
     static std::mutex mu;
@@ -576,16 +603,16 @@ Plan make_plan(size_t M, size_t dsub, size_t n_tiles, int sms)
     {
         std::lock_guard<std::mutex> lock(mu);
         for (const Entry &e : cache)
-            if (e.M == M && e.dsub == dsub && e.n_tiles == n_tiles && e.sms == sms) return e.plan;
+            if (e.M == M && e.dsub == dsub && e.n_tiles == n_tiles && e.sms == sms && e.marg_rings == marg_rings) return e.plan;
     }
-    const Plan plan = make_plan_uncached(M, dsub, n_tiles, sms);
+    const Plan plan = make_plan_uncached(M, dsub, n_tiles, sms, marg_rings);
     std::lock_guard<std::mutex> lock(mu);
     if (cache.size() >= 32) cache.erase(cache.begin());
-    cache.push_back(Entry{M, dsub, n_tiles, sms, plan});
+    cache.push_back(Entry{M, dsub, n_tiles, sms, marg_rings, plan});
     return plan;
 }
 
-Plan make_plan_uncached(size_t M, size_t dsub, size_t n_tiles, int sms)
+Plan make_plan_uncached(size_t M, size_t dsub, size_t n_tiles, int sms, int marg_rings)
 {
     Plan best;
     unsigned long long best_span = ~0ull;
@@ -603,7 +630,7 @@ Plan make_plan_uncached(size_t M, size_t dsub, size_t n_tiles, int sms)
         int stages = 0;
         size_t smem = 0;
         for (int s = 4; s >= 2 && !stages; s--) {
-            smem = gm * b_bytes + (size_t)kXStages * kTile * pitch_b + (size_t)s * a_bytes + (size_t)kMargRing * kTile * 4 + 24 * 8;
+            smem = gm * b_bytes + (size_t)kXStages * kTile * pitch_b + (size_t)s * a_bytes + (size_t)marg_rings * kMargRing * kTile * 4 + 24 * 8;
             if (smem <= (size_t)kSmemLimit - 1024) stages = s;
         }
         if (!stages) continue;
@@ -687,7 +714,7 @@ rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const flo
                    const RotatedInput *rot, cudaStream_t stream)
 {
     const size_t n_tiles = ceil_div(n, (size_t)kTile);
-    const Plan plan = make_plan(cb.M, cb.dsub, n_tiles, device_sm_count());
+    const Plan plan = make_plan(cb.M, cb.dsub, n_tiles, device_sm_count(), rot ? 3 : 1);
     EncParams p;
     p.x = x;
     p.n = (long long)n;
@@ -716,7 +743,7 @@ rb_status launch_t(const DeviceCodebook &cb, const TensorOperands &tc, const flo
     for (int g = 0; g <= kMaxGroups; g++) p.cta_start[g] = plan.cta_start[g < plan.n_groups ? g : plan.n_groups];
     CUtensorMap tmap;
     RB_TRY(make_x_tensor_map(x, n, cb.M * cb.dsub, ldx, (size_t)plan.pitch_f, &tmap));
-    auto kern = encode_tc_kernel<DSUB>;
+    auto kern = rot ? encode_tc_kernel<DSUB, true> : encode_tc_kernel<DSUB, false>;
     RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
 #ifdef RB_TC_PHASES
     const bool trace = getenv("RB_TC_TRACE") != nullptr;
