@@ -294,6 +294,33 @@ def test_rotated_tensor_encode_adversarial(oracle, M, k, dsub, xscale):
     assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ in rows {np.unique(np.nonzero(codes != want)[0])[:10]}"
 
 
+def test_tensor_rotation_on_padded_views(oracle):
+    """Device views with a row pitch larger than d on both sides of the tensor rotation (TMA tensor maps with a
+    pitch, the exact re-rotation reading the padded rows): codes equal to the oracle's, reconstruction within 1e-5."""
+    import torch
+
+    n, M, k, dsub = 5_000, 30, 256, 10
+    d = M * dsub
+    q, r, x = random_codebook(M, k, dsub, 91), orthonormal(d, 92), normal((n, d), 93)
+    pq = rb.Pq(r, q)
+    xp = torch.zeros((n, d + 12), device="cuda")
+    xp[:, :d] = torch.from_numpy(x).cuda()
+    codes = torch.empty((n, M), dtype=torch.uint8, device="cuda")
+    recp = torch.full((n, d + 20), 7.0, device="cuda")
+    rb.set_project_algo(rb.PROJECT_TENSOR)
+    try:
+        pq.quantize_batch_into(xp[:, :d], codes)
+        pq.reconstruct_batch_into(codes, recp[:, :d])
+    finally:
+        rb.set_project_algo(rb.PROJECT_AUTO)
+    want = oracle.quantize_batch(q, r, x, np.uint8, n_threads=8)
+    assert np.array_equal(codes.cpu().numpy(), want)
+    want_rec = oracle.reconstruct_batch(q, r, want, n_threads=8)
+    rec = recp[:, :d].cpu().numpy()
+    assert np.abs(rec - want_rec).max() <= 1e-5 * np.abs(want_rec).max()
+    assert bool((recp[:, d:] == 7.0).all())      # nothing written past the view
+
+
 @pytest.mark.parametrize("n,M,dsub", [(400_000, 16, 8), (150_000, 30, 10)])
 def test_tensor_rotation_many_units_per_cta(n, M, dsub):
     """Long runs of (tile, column group) units per CTA: the operand rings wrap many times (a converter set that skipped
