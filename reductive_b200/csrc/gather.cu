@@ -311,6 +311,8 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
         int cons = 0, gw = 0, W = 0, n_groups = 0, tile_rows = 0, stages = 0;
         size_t smem = 0;
     };
+    // development knobs for scripts/gather_time.py sweeps (not part of the ABI): force the block shape, cap the group
+    // width, set the ring depth
     static const int env_big = getenv("RB_GATHER_BIG") ? atoi(getenv("RB_GATHER_BIG")) : -1;
     static const int env_w = getenv("RB_GATHER_W") ? atoi(getenv("RB_GATHER_W")) : 0;
     static const int env_stages = getenv("RB_GATHER_STAGES") ? atoi(getenv("RB_GATHER_STAGES")) : 0;
