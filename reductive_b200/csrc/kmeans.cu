@@ -258,7 +258,7 @@ ordered_sum_kernel(const float *__restrict__ x, long long ldx, long long n, int 
 //     the same chunk at the same time, the chunk's rows (< 96 MB, inside L2) are fetched from HBM once although
 //     each (row, subquantizer) piece is gathered by a different warp.  `init` (or nullptr) continues chains started
 //     on another rank: data-parallel training can pass the running sums from rank to rank and stay bit-identical.
-constexpr int kLocalThreads = 512;
+constexpr int kLocalThreads = 1024;  // one block per SM (shared memory): 32 warps hide the serial placement steps
 constexpr int kLocalWarps = kLocalThreads / 32;
 
 // rows per chunk: a power of two in [4096, 65536] (u16 offsets) whose x rows (4*d bytes each) stay below ~96 MB of L2
@@ -279,8 +279,9 @@ __device__ __forceinline__ unsigned same_code_lanes(unsigned code, bool live)
     unsigned peers = __ballot_sync(0xffffffffu, live);
 #pragma unroll
     for (int b = 0; b < 8; b++) {
-        const unsigned v = __ballot_sync(0xffffffffu, (code >> b) & 1u);
-        peers &= ((code >> b) & 1u) ? v : ~v;
+        const unsigned bit = (code >> b) & 1u;
+        const unsigned v = __ballot_sync(0xffffffffu, bit);
+        peers &= v ^ (bit - 1u);  // one three-input logic op: lanes whose bit b equals mine
     }
     return peers;
 }
