@@ -25,12 +25,14 @@
 //   The emitted codes are therefore identical to the exact kernel's (and the oracle's) for every input.
 //
 // Data flow of one CTA (persistent, one per SM, 14 warps):
-//   warp 0      producer: per row tile, one cp.async.bulk (TMA engine) per row copies the tile's column slice
-//               (a group of subquantizers) into shared memory; loads the group's B operands when the group changes
-//   warps 2-5   converters: thread = row; split the FP32 subvector into FP16 limbs, write the A operand in the
+//   warp 13     producer: the group's B operands once (cp.async.bulk), then one TMA tensor-map tile load per row tile
+//               (128 rows x the group's column slice, pitch an odd multiple of 16 bytes)
+//   warps 8-11  converters: thread = row; split the FP32 subvector into FP16 limbs, write the A operand in the
 //               no-swizzle K-major core-matrix layout, publish the row's margin
-//   warp 1      one thread issues tcgen05.mma (K/16 instructions per unit) and tcgen05.commit
-//   warps 6-13  epilogue, two sets of four warps alternating over the two 256-column accumulators
+//   warp 12     one thread issues tcgen05.mma (K/16 instructions per unit) and tcgen05.commit
+//   warps 0-7   epilogue, two sets of four warps alternating over the two 256-column accumulators
+// A rotated input (x ~ x0 . R from project_tc.cu, template parameter ROT) widens the margin by the rotation's error
+// bound and collects the undecided rows per subquantizer for an exact re-rotation (encode_tc.cuh RotatedInput).
 // Bounds (C2: 2M x 300, M=30): HBM 4*d + M bytes per vector is the roofline (0.38 ms); the kernel is bound by the
 // CUDA-core scan of the 128 x 256 accumulator (1 min3 per element and partition), see DESIGN.md.
 #include <cuda.h>
