@@ -24,7 +24,8 @@
 //   atomic: shared-memory atomics, summation order unspecified (FP32 order-of-summation error ~1e-7 relative);
 //     used for k > 1024.
 // Across ranks (data-parallel k-means) the all-reduce adds per-rank partial sums, which is not the
-// single sequential chain either: multi-GPU training is tolerance-level (1e-4), single-GPU is bit-exact.
+// single sequential chain: that mode is tolerance-level.  The `init` argument of the ordered path continues
+// chains begun on the preceding rank, which keeps multi-GPU training bit-exact (dist.py mode="chained").
 // Counts follow the reference's f32 `+= 1.0` (exact to 2^24 per cluster, kmeans.rs:188).
 #include "common.cuh"
 

@@ -9,8 +9,10 @@
 //
 // Bound: FP32 FMA pipe (2*d^2 flop per row).  project_fast_kernel is a register-tiled SIMT SGEMM (128 x 64 block
 // tile, 8 x 4 per thread, K steps of 16 through a 3-stage cp.async ring, 16-byte global and shared accesses);
-// project_kernel is the general-stride fallback.  A tcgen05 3xBF16 split would be several times faster still but
-// not bit-identical; it is listed as follow-up work in DESIGN.md.
+// project_kernel is the general-stride fallback.  Large aligned batches go through the tcgen05 two-limb GEMM in
+// project_tc.cu instead (not bit-identical: decode uses it within 1e-5, encode re-rotates what it cannot certify
+// with the order implemented here); this file remains the exact path for small batches, OPQ training and
+// rb_project_rows.
 #include "common.cuh"
 
 namespace rb {
