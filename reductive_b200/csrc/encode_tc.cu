@@ -189,6 +189,37 @@ struct EncParams {
     unsigned short cta_start[kMaxGroups + 1];  // CTAs [cta_start[g], cta_start[g+1]) own column group g
 };
 
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(unsigned long long v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float hi2(unsigned long long v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 {
     float r;
@@ -390,18 +421,20 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                 for (int h = 0; h < 2; h++) {
                     if (ml0 + h >= gm_cur) break;
                     const float *sub = xv + h * DSUB;
-                    float xs = 0.f;
+                    unsigned long long xs2 = 0ull;  // ||x||^2 as two interleaved partial sums (only the margin uses it)
                     uint32_t hw[DSUB / 2], lw[DSUB / 2];
 #pragma unroll
                     for (int t2 = 0; t2 < DSUB / 2; t2++) {
                         const float a0 = sub[2 * t2], a1 = sub[2 * t2 + 1];
-                        xs = fmaf(a0, a0, xs);
-                        xs = fmaf(a1, a1, xs);
-                        const float s0 = a0 * scale, s1 = a1 * scale;
-                        // two-limb FP16 split, two elements per conversion instruction
+                        xs2 = fma2(pack2(a0, a1), pack2(a0, a1), xs2);
+                        // packed FP32 (mul / fma .f32x2) on the element pair; two-limb FP16 split, two elements per
+                        // conversion instruction
+                        const unsigned long long s2 = mul2(pack2(a0, a1), pack2(scale, scale));
+                        const float s0 = lo2(s2), s1 = hi2(s2);
                         const __half2 hh = __floats2half2_rn(s0, s1);
                         const float2 hf = __half22float2(hh);
-                        const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+                        const unsigned long long l2 = fma2(pack2(hf.x, hf.y), pack2(-1.f, -1.f), s2);  // s - hf, one rounding
+                        const __half2 ll = __floats2half2_rn(lo2(l2), hi2(l2));
                         hw[t2] = *reinterpret_cast<const uint32_t *>(&hh);
                         lw[t2] = *reinterpret_cast<const uint32_t *>(&ll);
                     }
@@ -419,6 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     // NaN in x makes xs NaN, Inf makes it Inf; |x * scale| <= sqrt(xs) * scale must stay inside the
                     // FP16 range (2^15) and, for padded codebooks, real scores must stay far below kPadScore
                     // (cs + 2 |x||c| <= 64 + 2 * 8 * sqrt(xs_sc) < 16 384 for xs_sc < 10^6): decide other rows exactly
+                    const float xs = lo2(xs2) + hi2(xs2);
                     const float xs_sc = xs * scale2;
                     const bool bad = cb_bad || !(xs_sc < p.xs_limit);
                     const float csmax = p.consts[g * p.gm + ml0 + h];
@@ -535,13 +569,18 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                 const float thr = m1 + marg;
                 const float SC = 1.099511627776e12f;  // 2^40
                 const float thr_sc = thr * SC;
-                float bs[4] = {0.f, 0.f, 0.f, 0.f}, as4[4] = {0.f, 0.f, 0.f, 0.f};
+                // packed FP32 FMA (fma.rn.f32x2): lanes = two consecutive positions, the same weight pairs serve both
+                // partitions; four partial sums keep the dependency chains short
+                unsigned long long bs2[2] = {0ull, 0ull}, as2[2] = {0ull, 0ull};
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    bs[i & 3] = fmaf(fma_sat(B[i], -SC, thr_sc), (float)(64 + i), bs[i & 3]);
-                    as4[i & 3] = fmaf(fma_sat(A[i], -SC, thr_sc), (float)(64 + i), as4[i & 3]);
+                for (int i = 0; i < 16; i += 2) {
+                    const unsigned long long w2 = pack2((float)(64 + i), (float)(65 + i));
+                    bs2[(i >> 1) & 1] = fma2(pack2(fma_sat(B[i], -SC, thr_sc), fma_sat(B[i + 1], -SC, thr_sc)), w2, bs2[(i >> 1) & 1]);
+                    as2[(i >> 1) & 1] = fma2(pack2(fma_sat(A[i], -SC, thr_sc), fma_sat(A[i + 1], -SC, thr_sc)), w2, as2[(i >> 1) & 1]);
                 }
-                const float accb = (bs[0] + bs[1]) + (bs[2] + bs[3]), acca = (as4[0] + as4[1]) + (as4[2] + as4[3]);
+                const float accb = (lo2(bs2[0]) + hi2(bs2[0])) + (lo2(bs2[1]) + hi2(bs2[1]));
+                const float acca = (lo2(as2[0]) + hi2(as2[0])) + (lo2(as2[1]) + hi2(as2[1]));
+
                 // one block and one chain below thr; |thr| large enough for exact t; NaN margins fail the comparisons
                 const bool certain = (fminf(accb, acca) >= 64.f) && (fmaxf(accb, acca) < 80.f) &&
                                      (fabsf(thr) >= 6.103515625e-5f) && (fabsf(m1) < 3.0e38f);
