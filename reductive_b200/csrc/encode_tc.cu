@@ -189,37 +189,6 @@ struct EncParams {
     unsigned short cta_start[kMaxGroups + 1];  // CTAs [cta_start[g], cta_start[g+1]) own column group g
 };
 
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
-{
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float lo2(unsigned long long v)
-{
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    return lo;
-}
-__device__ __forceinline__ float hi2(unsigned long long v)
-{
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    return hi;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
-{
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 {
     float r;

@@ -222,24 +222,29 @@ __global__ void __launch_bounds__(kPThreads, 1) project_tc_kernel(const __grid_c
 #pragma unroll
                 for (int i = 0; i < kKC / 4; i++) v[i] = *reinterpret_cast<const float4 *>(xr + ((i ^ (row & 7)) * 16));
                 uint32_t hw[kKC / 2], lw[kKC / 2];
-                float ss = 0.f, big = 0.f;
+                float big = 0.f;
+                unsigned long long ss2 = 0ull;  // the chunk's energy as two interleaved partial sums
+                const unsigned long long sx2 = pack2(sx, sx), neg2 = pack2(-1.f, -1.f);
 #pragma unroll
                 for (int i = 0; i < kKC / 4; i++) {
                     const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
-                        const float a0 = e[2 * h], a1 = e[2 * h + 1];
-                        ss = fmaf(a0, a0, ss);
-                        ss = fmaf(a1, a1, ss);
-                        const float s0 = a0 * sx, s1 = a1 * sx;
+                        // packed FP32 on the element pair (mul / fma .f32x2)
+                        const unsigned long long a2 = pack2(e[2 * h], e[2 * h + 1]);
+                        ss2 = fma2(a2, a2, ss2);
+                        const unsigned long long s2 = mul2(a2, sx2);
+                        const float s0 = lo2(s2), s1 = hi2(s2);
                         big = fmaxf(big, fmaxf(fabsf(s0), fabsf(s1)));
                         const __half2 hh = __floats2half2_rn(s0, s1);
                         const float2 hf = __half22float2(hh);
-                        const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+                        const unsigned long long l2 = fma2(pack2(hf.x, hf.y), neg2, s2);  // s - hf, one rounding
+                        const __half2 ll = __floats2half2_rn(lo2(l2), hi2(l2));
                         hw[2 * i + h] = *reinterpret_cast<const uint32_t *>(&hh);
                         lw[2 * i + h] = *reinterpret_cast<const uint32_t *>(&ll);
                     }
                 }
+                const float ss = lo2(ss2) + hi2(ss2);
                 // chunk energy; NaN marks a chunk the split cannot represent (NaN / Inf make ss itself non-finite)
                 if (want_err) se[c * kPT + row] = (big < kHalfLimit && ss < 3.0e38f) ? ss : __int_as_float(0x7fc00000);
                 mbar_wait(&a_empty[as], aph);
