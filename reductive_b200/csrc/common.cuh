@@ -51,6 +51,16 @@ cudaError_t pool_malloc(void **p, size_t bytes, cudaStream_t stream);
 
 static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
 
+// Number of SMs of the current device (launch geometry is sized from it; 148 on a B200).
+static inline int sm_count()
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0)
+        return 148;
+    return sms;
+}
+
 // ---------------------------------------------------------------------------------------------
 // device arithmetic that must round exactly like the reference's CPU code
 // ---------------------------------------------------------------------------------------------
@@ -175,6 +185,15 @@ rb_status launch_encode_recheck(const DeviceCodebook &cb, const float *x, ptrdif
                                 const uint32_t *pairs, const uint32_t *n_pairs, uint32_t max_pairs,
                                 void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs,
                                 cudaStream_t stream);
+
+// Pairs the tensor path could not decide: cands holds 4 words per pair (row, subquantizer, chain flags, block flags)
+// in `regions` regions of `region_cap` entries, region r holding region_counts[r] of them.  The candidates are the
+// centroids 16 b + a with chain a flagged (bit a / 2 + 16 (a % 2) of the chain word) and block b flagged (bit b or
+// bit 16 + b of the block word); both words all ones: every centroid.  Decides among them with the reference's
+// exact expression tree (first index on ties).
+rb_status launch_encode_candidates(const DeviceCodebook &cb, const float *x, ptrdiff_t ldx, const uint32_t *cands,
+                                   const uint32_t *region_counts, uint32_t regions, uint32_t region_cap, void *codes,
+                                   int code_width, ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream);
 
 // Flagged rows of a ROTATED batch, bucketed per subquantizer (counts[M], rows[M][n_cap]): re-rotate the subvector
 // exactly (reference sgemm order, x0 . r) and re-decide it with the reference's expression tree.

@@ -258,6 +258,66 @@ encode_recheck_kernel(const float *__restrict__ quantizers, const float *__restr
     }
 }
 
+// One thread per undecided (row, m) pair of the tensor filter: the candidates are the centroids j = 16 b + a for the
+// flagged chains a and blocks b (bit layout: common.cuh launch_encode_candidates; every other centroid is proven not
+// to be the reference's argmin; all ones = no proof, every centroid).  Same expression tree as encode_exact_kernel; smaller distance wins,
+// equal distances -> smaller index, NaN ranks largest (kmeans.rs:150-155).  The list comes in regions (one per
+// epilogue warp of the tensor kernel): a block walks whole regions.
+template <int DSUB>
+__global__ void __launch_bounds__(256)
+encode_candidates_kernel(const float *__restrict__ quantizers, const float *__restrict__ cs_all, int k,
+                         const float *__restrict__ x, long long ldx, const uint32_t *__restrict__ cands,
+                         const uint32_t *__restrict__ region_counts, uint32_t regions, uint32_t region_cap, void *codes,
+                         int code_width, long long crs, long long ccs)
+{
+    for (uint32_t r = blockIdx.x; r < regions; r += gridDim.x) {
+      const uint32_t cnt = min(region_counts[r], region_cap);
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(cands) + (size_t)r * region_cap + i);
+        const long long row = e.x;
+        const int m = (int)e.y;
+        const uint32_t ma = e.z, mb = (e.w | (e.w >> 16)) & 0xffffu;
+        const float *xr = x + row * ldx + (long long)m * DSUB;
+        float xv[DSUB];
+        if constexpr (DSUB % 2 == 0) {  // the tensor path requires ldx % 4 == 0 and even dsub: 8-byte aligned
+#pragma unroll
+            for (int t = 0; t < DSUB; t += 2) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(xr + t));
+                xv[t] = v.x;
+                xv[t + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < DSUB; t++) xv[t] = __ldg(xr + t);
+        }
+        const float xs = unrolled_sqnorm_reg<DSUB>(xv);
+        const float *qm = quantizers + (size_t)m * k * DSUB;
+        const float *csg = cs_all + (size_t)m * k;
+        int best = -1;
+        float bv = 0.f;
+        for (uint32_t bb = mb; bb; bb &= bb - 1) {  // ascending blocks, ascending chains: ascending j
+            const int b = __ffs(bb) - 1;
+            for (int a = 0; a < 16; a++) {
+                if (!((ma >> ((a >> 1) + ((a & 1) << 4))) & 1u)) continue;
+                const int j = 16 * b + a;
+                if (j >= k) continue;
+                float c[DSUB];
+                load_centroid<DSUB>(qm + (size_t)j * DSUB, c);
+                float dp = 0.f;
+#pragma unroll
+                for (int t = 0; t < DSUB; t++) dp = __fmaf_rn(xv[t], c[t], dp);
+                const float d = ref_distance(xs, __ldg(csg + j), dp);
+                if (best < 0 || of_less(d, bv)) {  // j ascends: strict "less" keeps the first minimum
+                    bv = d;
+                    best = j;
+                }
+            }
+        }
+        if (best >= 0) store_code(codes, code_width, row * crs + (long long)m * ccs, (unsigned)best);
+      }
+    }
+}
+
 // Flagged rows of a rotated batch (tensor rotation + tensor encode, encode_tc.cuh RotatedInput), bucketed per
 // subquantizer.  blockIdx.y = subquantizer m: the block keeps R[:, m*DSUB .. +DSUB) and the m-th codebook in shared
 // memory and walks its share of the bucket, thread = flagged row:
@@ -382,7 +442,7 @@ rb_status launch_rotated_t(const DeviceCodebook &cb, const uint32_t *counts, con
     auto kern = rotated_recheck_kernel<DSUB>;
     if (smem > 48 * 1024) RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // a few blocks per subquantizer, each staging its operands once; about four blocks' worth of work per SM
-    unsigned per_m = (unsigned)ceil_div((size_t)148 * 4, cb.M);
+    unsigned per_m = (unsigned)ceil_div((size_t)sm_count() * 4, cb.M);
     const unsigned most = (unsigned)ceil_div(n_cap, (size_t)256);
     if (per_m > most) per_m = most;
     if (per_m < 1) per_m = 1;
@@ -404,9 +464,10 @@ rb_status launch_t(const DeviceCodebook &cb, const float *x, size_t n, ptrdiff_t
     kch = kch > k ? k : (kch / 8) * 8;
     const size_t smem = (size_t)kch * (DSUB + 1) * sizeof(float);
     const size_t row_tiles = ceil_div(n, (size_t)kThreads * RPT);
-    // enough blocks to fill 148 SMs a few times over: split the subquantizers when there are few row tiles
+    // enough blocks to fill the SMs a few times over: split the subquantizers when there are few row tiles
     int m_per_block = M;
-    while (m_per_block > 1 && row_tiles * ceil_div(M, m_per_block) < 148 * 4) m_per_block = (m_per_block + 1) / 2;
+    const int sms = sm_count();
+    while (m_per_block > 1 && row_tiles * ceil_div(M, m_per_block) < (size_t)sms * 4) m_per_block = (m_per_block + 1) / 2;
     dim3 grid((unsigned)row_tiles, (unsigned)ceil_div(M, m_per_block));
     encode_exact_kernel<DSUB, RPT><<<grid, kThreads, smem, stream>>>(
         cb.quantizers, cb.cs, M, k, kch, x, (long long)n, (long long)ldx, codes, code_width, (long long)crs,
@@ -444,7 +505,8 @@ rb_status launch_encode_exact_gated(const DeviceCodebook &cb, const float *x, si
     const int M = (int)cb.M;
     const size_t row_tiles = ceil_div(n, (size_t)kThreads);
     int m_per_block = M;
-    while (m_per_block > 1 && row_tiles * ceil_div(M, m_per_block) < 148 * 4) m_per_block = (m_per_block + 1) / 2;
+    const int sms = sm_count();
+    while (m_per_block > 1 && row_tiles * ceil_div(M, m_per_block) < (size_t)sms * 4) m_per_block = (m_per_block + 1) / 2;
     dim3 grid((unsigned)row_tiles, (unsigned)ceil_div(M, m_per_block));
     encode_exact_generic_kernel<<<grid, kThreads, 0, stream>>>(cb.quantizers, cb.cs, M, (int)cb.k, (int)cb.dsub, x,
                                                              (long long)n, (long long)ldx, codes, code_width,
@@ -494,12 +556,36 @@ rb_status launch_rotated_recheck(const DeviceCodebook &cb, const uint32_t *count
     return RB_ERR_UNSUPPORTED;
 }
 
+rb_status launch_encode_candidates(const DeviceCodebook &cb, const float *x, ptrdiff_t ldx, const uint32_t *cands,
+                                   const uint32_t *region_counts, uint32_t regions, uint32_t region_cap, void *codes,
+                                   int code_width, ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream)
+{
+    if (regions == 0) return RB_OK;
+    unsigned blocks = (unsigned)sm_count() * 8;
+    if (blocks > regions) blocks = regions;
+    switch (cb.dsub) {
+#define X(D)                                                                                                             \
+    case D:                                                                                                              \
+        encode_candidates_kernel<D><<<blocks, 256, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.k, x, (long long)ldx, cands, \
+                                                                region_counts, regions, region_cap, codes, code_width,  \
+                                                                (long long)crs, (long long)ccs);                        \
+        break;
+        RB_ROT_DSUBS(X)
+#undef X
+    default:
+        set_error("candidate recheck: subvector width %zu is not instantiated", cb.dsub);
+        return RB_ERR_UNSUPPORTED;
+    }
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
 rb_status launch_encode_recheck(const DeviceCodebook &cb, const float *x, ptrdiff_t ldx, const uint32_t *pairs,
                                 const uint32_t *n_pairs, uint32_t max_pairs, void *codes, int code_width,
                                 ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream)
 {
     if (max_pairs == 0) return RB_OK;
-    encode_recheck_kernel<<<148 * 4, 256, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.k, (int)cb.dsub, x,
+    encode_recheck_kernel<<<(unsigned)sm_count() * 4, 256, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.k, (int)cb.dsub, x,
                                                         (long long)ldx, pairs, n_pairs, max_pairs, codes, code_width,
                                                         (long long)crs, (long long)ccs);
     RB_LAUNCH_CHECK();

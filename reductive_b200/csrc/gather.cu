@@ -397,7 +397,7 @@ bool launch_tiled(const DeviceCodebook &cb, const void *codes, int code_width, s
 
     // one resident wave: as many strips as clusters (or blocks) fit on the device at once
     const long long n_tiles = (long long)ceil_div(n, (size_t)tile_rows);
-    long long strips = (blocks_per_sm * 148) / n_groups;
+    long long strips = ((long long)blocks_per_sm * sm_count()) / n_groups;
     if (lockstep) {
         int max_clusters = 0;
         cfg.gridDim = dim3((unsigned)(strips * n_groups));
@@ -462,7 +462,7 @@ rb_status launch_pw(const DeviceCodebook &cb, const void *codes, int code_width,
     const size_t smem = smem_cb ? (size_t)m_per_group * per_m : 0;
 
     // row strips: 2 waves of 2 blocks/SM over all groups, at least 64 rows each
-    size_t strips = ceil_div((size_t)148 * 4, (size_t)n_groups);
+    size_t strips = ceil_div((size_t)sm_count() * 4, (size_t)n_groups);
     size_t rows_per_block = ceil_div(n, strips);
     if (rows_per_block < 64) rows_per_block = 64;
     strips = ceil_div(n, rows_per_block);

@@ -561,7 +561,7 @@ rb_status launch_acc_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT *cod
     const size_t smem = k * pad * sizeof(float) + k * sizeof(int);
     const bool smem_acc = smem <= 160 * 1024;
     // ~4 blocks per SM across all subquantizers, at least 1024 rows per block
-    size_t chunks = ceil_div((size_t)148 * 4, M);
+    size_t chunks = ceil_div((size_t)sm_count() * 4, M);
     size_t rows_per_block = ceil_div(n, chunks);
     if (rows_per_block < 1024) rows_per_block = 1024;
     chunks = ceil_div(n, rows_per_block);
@@ -587,7 +587,7 @@ rb_status launch_ordered_t(const float *x, size_t n, ptrdiff_t ldx, const CodeT 
                            size_t dsub, float *packed, cudaStream_t stream)
 {
     // chunks: about 2 waves of warps over the GPU, at least 256 rows per chunk
-    size_t n_chunks = ceil_div((size_t)148 * 64, M);
+    size_t n_chunks = ceil_div((size_t)sm_count() * 64, M);
     size_t rows_per_chunk = ceil_div(n, n_chunks);
     if (rows_per_chunk < 256) rows_per_chunk = 256;
     n_chunks = ceil_div(n, rows_per_chunk);

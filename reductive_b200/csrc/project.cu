@@ -264,7 +264,7 @@ rb_status launch_pack_rows(const float *src, size_t n, size_t d, ptrdiff_t rs, p
                            cudaStream_t stream)
 {
     if (n == 0 || d == 0) return RB_OK;
-    pack_rows_kernel<<<148 * 8, 256, 0, stream>>>(src, (long long)n, (long long)d, (long long)rs, (long long)cs, dst);
+    pack_rows_kernel<<<(unsigned)sm_count() * 8, 256, 0, stream>>>(src, (long long)n, (long long)d, (long long)rs, (long long)cs, dst);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }
@@ -273,7 +273,7 @@ rb_status launch_unpack_rows(const float *src, size_t n, size_t d, float *dst, p
                              cudaStream_t stream)
 {
     if (n == 0 || d == 0) return RB_OK;
-    unpack_rows_kernel<<<148 * 8, 256, 0, stream>>>(src, (long long)n, (long long)d, dst, (long long)rs,
+    unpack_rows_kernel<<<(unsigned)sm_count() * 8, 256, 0, stream>>>(src, (long long)n, (long long)d, dst, (long long)rs,
                                                     (long long)cs);
     RB_LAUNCH_CHECK();
     return RB_OK;

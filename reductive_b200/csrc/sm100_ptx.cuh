@@ -79,10 +79,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// The whole retry loop lives in one asm block: a failed try sleeps in hardware (suspend-time hint) and a retry costs
+// the try itself and one branch -- a C-level loop around mbar_try_wait re-materialised the address and parity on every
+// iteration, and the spinning warps took a quarter of all issued instructions (ncu, encode_tc_kernel).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "RB_MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra RB_MBAR_DONE_%=;\n\t"
+        "bra RB_MBAR_WAIT_%=;\n\t"
+        "RB_MBAR_DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+
+// Busy-polling wait (no suspend-time hint): lowest wake-up latency, for waits on the critical path of a pipeline.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "RB_MBAR_SPIN_%=:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra RB_MBAR_SPUN_%=;\n\t"
+        "bra RB_MBAR_SPIN_%=;\n\t"
+        "RB_MBAR_SPUN_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // ---- thread-block clusters --------------------------------------------------------------------------------
@@ -202,6 +226,30 @@ __device__ __forceinline__ void mma_f16_ss_lohi(uint32_t d_tmem, uint32_t a_lo, 
         "setp.ne.b32 p, %6, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Whole-warp variants: every lane executes the call (so descriptors and addresses stay warp-uniform and live in
+// uniform registers), one elected lane issues the instruction.
+__device__ __forceinline__ void mma_f16_ss_lohi_warp(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                     uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_warp(uint64_t *bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
         : "memory");
 }
 
