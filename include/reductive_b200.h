@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 1
+#define RB_ABI_VERSION 2
 
 /* Status codes.  1..6 mirror ReductiveError (src/error.rs:6-41); 16.. are the reference's panics
  * (assert sites: primitives.rs:25-34,74-87,123-135,159-167; pq.rs:39-55; kmeans.rs:61-71,269-277),
@@ -51,7 +51,8 @@ typedef enum rb_status {
     RB_ERR_K_MEANS_K = 20,            /* k == 0 or k >= n instances (kmeans.rs:61-67)              */
     RB_ERR_CUDA = 32,                 /* a CUDA runtime call or kernel failed                      */
     RB_ERR_NO_DEVICE = 33,            /* no CUDA device visible                                    */
-    RB_ERR_UNSUPPORTED = 34           /* shape outside what the kernels cover (message says what)  */
+    RB_ERR_UNSUPPORTED = 34,          /* shape outside what the kernels cover (message says what)  */
+    RB_ERR_NCCL = 35                  /* an NCCL call failed / libnccl.so.2 could not be loaded    */
 } rb_status;
 
 typedef enum rb_mem_kind { RB_MEM_HOST = 0, RB_MEM_DEVICE = 1 } rb_mem_kind;
@@ -205,6 +206,57 @@ rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t row_
 rb_status rb_project_rows(const float *x, size_t n, size_t d, ptrdiff_t x_row_stride,
                           ptrdiff_t x_col_stride, const float *r_dev, int transpose_r, float *out,
                           void *stream);
+
+/* ---- multi-GPU training (data-parallel Pq k-means; NCCL is called inside the library) ------------- */
+
+/* The reference trains the M subquantizers as M independent Rayon tasks (pq.rs:226-241), each a sequential k-means
+ * (kmeans.rs:263-327).  Across G GPUs the two phases of an iteration are sharded on different axes:
+ *   cluster_assignments (kmeans.rs:319): by ROWS    -- rank r assigns its own rows against all M codebooks;
+ *   update_centroids    (kmeans.rs:320): by SUBQUANTIZERS -- rank r owns subquantizers rb_dist_subquantizer_range(r)
+ *     and adds all n rows of every cluster sequentially in row order, which is exactly the reference's f32 chain
+ *     (kmeans.rs:185-189): trained centroids are BIT-IDENTICAL to a one-GPU run for any G.
+ * Rank r's rows follow rank r-1's in the reference's row order.  Exchanges: the column slices of the training matrix
+ * once (when the state is created), then per iteration the u8 assignments (all-to-all, n*M bytes in total) and the
+ * new centroids (all-gather). */
+typedef struct rb_comm rb_comm;               /* one rank of an NCCL communicator, bound to the current device */
+typedef struct rb_kmeans_dist rb_kmeans_dist; /* both layouts of the training rows + exchange buffers of one run */
+
+/* Subquantizers [*m_begin, *m_end) whose centroid update rank `rank` of `world` owns (host only). */
+rb_status rb_dist_subquantizer_range(size_t n_subquantizers, int rank, int world, size_t *m_begin, size_t *m_end);
+
+/* ncclGetUniqueId into id_out (len >= 128); rank 0 creates it and hands it to the other ranks by any means. */
+rb_status rb_comm_unique_id(void *id_out, size_t len);
+/* ncclCommInitRank on the CURRENT device (collective over the `world` ranks). */
+rb_status rb_comm_create(const void *id, int rank, int world, rb_comm **out);
+void rb_comm_destroy(rb_comm *comm);
+int rb_comm_rank(const rb_comm *comm);
+int rb_comm_world(const rb_comm *comm);
+
+/* x_local: DEVICE [n_local, M*dsub] with row stride x_row_stride, borrowed for the lifetime of the state (the rows
+ * must not change: k-means never modifies its instances).  Collective: exchanges the row counts and the column
+ * slices of the training matrix. */
+rb_status rb_kmeans_dist_create(rb_comm *comm, const float *x_local, size_t n_local, ptrdiff_t x_row_stride,
+                                size_t n_subquantizers, size_t n_centroids, size_t subquantizer_dim, void *stream,
+                                rb_kmeans_dist **out);
+/* One KMeansIteration::kmeans_iteration (kmeans.rs:308-327) for all M subquantizers over the rows of all ranks.
+ * centroids: DEVICE [M,k,dsub], identical on every rank on entry and on exit (updated in place); loss_or_null:
+ * DEVICE [M].  Collective, asynchronous on `stream`. */
+rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *state, float *centroids, float *loss_or_null, void *stream);
+void rb_kmeans_dist_destroy(rb_kmeans_dist *state);
+
+/* TrainPq::train_pq_using for Pq (pq.rs:201-249) over rows sharded across the ranks of `comm`; every rank passes
+ * its own rows (instances_local: [n_local, d], mem_kind; unit column stride) and the same initial centroids (HOST
+ * [n_attempts, M, k, dsub]) and receives the same quantizer.  n_total = rows of all ranks (validated). */
+rb_status rb_pq_train_dist(rb_comm *comm, const float *instances_local, size_t n_local, size_t n_total, size_t d,
+                           ptrdiff_t row_stride, size_t n_subquantizers, uint32_t n_subquantizer_bits,
+                           size_t n_iterations, size_t n_attempts, const float *initial_centroids, float *loss_out,
+                           int mem_kind, void *stream, rb_pq **out);
+/* The same from ONE process: instances HOST [n, d] are split into contiguous row blocks over `devices`
+ * (ncclCommInitAll, one host thread per device).  The returned quantizer lives on devices[0]. */
+rb_status rb_pq_train_multi(const int *devices, int n_devices, const float *instances, size_t n, size_t d,
+                            ptrdiff_t row_stride, size_t n_subquantizers, uint32_t n_subquantizer_bits,
+                            size_t n_iterations, size_t n_attempts, const float *initial_centroids, float *loss_out,
+                            rb_pq **out);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,7 @@ ERR_K_MEANS_K = 20
 ERR_CUDA = 32
 ERR_NO_DEVICE = 33
 ERR_UNSUPPORTED = 34
+ERR_NCCL = 35
 
 MEM_HOST, MEM_DEVICE = 0, 1
 ENCODE_AUTO, ENCODE_EXACT, ENCODE_TENSOR = 0, 1, 2
@@ -44,6 +45,9 @@ EXPORTED_SYMBOLS = [
     "rb_kmeans_assign_accumulate_from", "rb_kmeans_code_pitch", "rb_kmeans_code_width", "rb_kmeans_assign",
     "rb_kmeans_accumulate",
     "rb_kmeans_finalize", "rb_pq_train", "rb_project_rows",
+    "rb_dist_subquantizer_range", "rb_comm_unique_id", "rb_comm_create", "rb_comm_destroy", "rb_comm_rank",
+    "rb_comm_world", "rb_kmeans_dist_create", "rb_kmeans_dist_iterate", "rb_kmeans_dist_destroy", "rb_pq_train_dist",
+    "rb_pq_train_multi",
 ]
 
 
@@ -132,6 +136,20 @@ def _load() -> C.CDLL:
     lib.rb_kmeans_finalize.argtypes = [fp, sz, sz, sz, C.c_uint64, fp, fp, vp]
     lib.rb_pq_train.argtypes = [fp, sz, sz, pd, pd, sz, C.c_uint32, sz, sz, fp, fp, C.c_int, vp, C.POINTER(vp)]
     lib.rb_project_rows.argtypes = [fp, sz, sz, pd, pd, fp, C.c_int, fp, vp]
+    lib.rb_dist_subquantizer_range.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
+    lib.rb_comm_unique_id.argtypes = [vp, sz]
+    lib.rb_comm_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.rb_comm_destroy.argtypes = [vp]
+    lib.rb_comm_destroy.restype = None
+    lib.rb_comm_rank.argtypes = [vp]
+    lib.rb_comm_world.argtypes = [vp]
+    lib.rb_kmeans_dist_create.argtypes = [vp, fp, sz, pd, sz, sz, sz, vp, C.POINTER(vp)]
+    lib.rb_kmeans_dist_iterate.argtypes = [vp, fp, fp, vp]
+    lib.rb_kmeans_dist_destroy.argtypes = [vp]
+    lib.rb_kmeans_dist_destroy.restype = None
+    lib.rb_pq_train_dist.argtypes = [vp, fp, sz, sz, sz, pd, sz, C.c_uint32, sz, sz, fp, fp, C.c_int, vp, C.POINTER(vp)]
+    lib.rb_pq_train_multi.argtypes = [C.POINTER(C.c_int), C.c_int, fp, sz, sz, pd, sz, C.c_uint32, sz, sz, fp, fp,
+                                      C.POINTER(vp)]
     return lib
 
 
@@ -159,6 +177,8 @@ def check(status: int) -> None:
         raise NoDeviceError(msg)
     if status == ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
+    if status == ERR_NCCL:
+        raise CudaError(f"NCCL: {msg}")
     raise CudaError(f"rb_status {status}: {msg}")
 
 

@@ -1,0 +1,494 @@
+// dist.cu — data-parallel Pq k-means across GPUs behind the C ABI; NCCL is called from here (include/reductive_b200.h,
+// "multi-GPU" section).
+//
+// Replaces, for rows sharded over G GPUs, the loop of kmeans_with_centroids (src/kmeans.rs:263-288) around
+// kmeans_iteration (src/kmeans.rs:308-327) for all M subquantizers of Pq::train_pq_using (src/pq/pq.rs:201-249).
+//
+// The two phases of an iteration are sharded on DIFFERENT axes:
+//   assignment (kmeans.rs:319)      rows: rank r assigns its n_r rows against all M codebooks (no exchange);
+//   update_centroids (kmeans.rs:320) subquantizers: rank r owns M/G subquantizers and adds ALL n rows of each
+//     cluster sequentially in row order — exactly the reference's f32 chain (kmeans.rs:185-189), so trained centroids
+//     are bit-identical to a one-GPU run (and to the oracle) for any G.  This is the reference's own parallel axis
+//     (Rayon over subquantizers, pq.rs:226-241).
+// The training rows never change, so each rank receives the column slice x[:, its subquantizers] of every other
+// rank ONCE (an all-to-all of the training matrix when the state is created) and keeps both layouts.  Per iteration
+// only the assignments travel (all-to-all of u8 codes, n * M bytes in total) and the new centroids are
+// all-gathered (M * k * dsub floats).  Everything is stream-ordered on the caller's stream.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rb {
+namespace {
+
+// NCCL is resolved at run time (libnccl.so.2): a process that already carries one (torch) keeps using that copy.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+const NcclApi &nccl()
+{
+    static NcclApi api = []() {
+        NcclApi a;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return a;
+#define RB_SYM(name) a.name = reinterpret_cast<decltype(a.name)>(dlsym(h, "nccl" #name))
+        RB_SYM(GetUniqueId); RB_SYM(CommInitRank); RB_SYM(CommInitAll); RB_SYM(CommDestroy); RB_SYM(GroupStart);
+        RB_SYM(GroupEnd); RB_SYM(Send); RB_SYM(Recv); RB_SYM(Broadcast); RB_SYM(AllGather); RB_SYM(GetErrorString);
+#undef RB_SYM
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Send &&
+               a.Recv && a.Broadcast && a.AllGather && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+
+#define RB_NCCL_TRY(expr)                                                                                        \
+    do {                                                                                                         \
+        ncclResult_t _r = (expr);                                                                                \
+        if (_r != ncclSuccess) {                                                                                 \
+            ::rb::set_error("%s failed: %s (%s:%d)", #expr, nccl().GetErrorString(_r), __FILE__, __LINE__);      \
+            return RB_ERR_NCCL;                                                                                  \
+        }                                                                                                        \
+    } while (0)
+
+rb_status require_nccl()
+{
+    if (!nccl().ok) {
+        set_error("libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+        return RB_ERR_NCCL;
+    }
+    return RB_OK;
+}
+
+}  // namespace
+}  // namespace rb
+
+using namespace rb;
+
+struct rb_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+};
+
+// Per-run state of the sharded k-means: both layouts of the training rows and the exchange buffers.
+struct rb_kmeans_dist {
+    rb_comm *c = nullptr;
+    size_t M = 0, k = 0, dsub = 0, d = 0;
+    const float *x_local = nullptr;  // borrowed: [n_local, d], row pitch ldx
+    ptrdiff_t ldx = 0;
+    size_t n_local = 0, n_total = 0;
+    std::vector<size_t> n_of, row_off;  // per rank
+    std::vector<size_t> m_lo;           // subquantizer ranges: rank r owns [m_lo[r], m_lo[r + 1])
+    float *xcol = nullptr;              // owned: [n_total, dcols] with dcols = (m_lo[rank + 1] - m_lo[rank]) * dsub
+    unsigned char *codes_local = nullptr, *codes_recv = nullptr, *codes_own = nullptr;
+    float *packed_own = nullptr, *loss_all = nullptr;
+    int code_width = 1;
+    size_t pitch_local = 0, pitch_total = 0;
+    size_t m_own() const { return m_lo[c->rank + 1] - m_lo[c->rank]; }
+};
+
+extern "C" {
+
+rb_status rb_dist_subquantizer_range(size_t n_subquantizers, int rank, int world, size_t *m_begin, size_t *m_end)
+{
+    if (world <= 0 || rank < 0 || rank >= world || !m_begin || !m_end) {
+        set_error("bad rank / world (%d / %d)", rank, world);
+        return RB_ERR_INVALID;
+    }
+    *m_begin = n_subquantizers * (size_t)rank / (size_t)world;
+    *m_end = n_subquantizers * (size_t)(rank + 1) / (size_t)world;
+    return RB_OK;
+}
+
+rb_status rb_comm_unique_id(void *id_out, size_t len)
+{
+    if (!id_out || len < sizeof(ncclUniqueId)) {
+        set_error("id buffer must hold %zu bytes", sizeof(ncclUniqueId));
+        return RB_ERR_INVALID;
+    }
+    RB_TRY(require_nccl());
+    ncclUniqueId id;
+    RB_NCCL_TRY(nccl().GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return RB_OK;
+}
+
+rb_status rb_comm_create(const void *id, int rank, int world, rb_comm **out)
+{
+    if (!out) return RB_ERR_INVALID;
+    *out = nullptr;
+    if (!id || world <= 0 || rank < 0 || rank >= world) {
+        set_error("bad communicator arguments (rank %d of %d)", rank, world);
+        return RB_ERR_INVALID;
+    }
+    RB_TRY(require_nccl());
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device visible; reductive_b200 has no CPU fallback");
+        return RB_ERR_NO_DEVICE;
+    }
+    rb_comm *c = new rb_comm();
+    c->rank = rank;
+    c->world = world;
+    cudaGetDevice(&c->device);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    const ncclResult_t r = nccl().CommInitRank(&c->comm, world, uid, rank);
+    if (r != ncclSuccess) {
+        set_error("ncclCommInitRank failed: %s", nccl().GetErrorString(r));
+        delete c;
+        return RB_ERR_NCCL;
+    }
+    *out = c;
+    return RB_OK;
+}
+
+void rb_comm_destroy(rb_comm *c)
+{
+    if (!c) return;
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    delete c;
+}
+
+int rb_comm_rank(const rb_comm *c) { return c ? c->rank : -1; }
+int rb_comm_world(const rb_comm *c) { return c ? c->world : 0; }
+
+void rb_kmeans_dist_destroy(rb_kmeans_dist *h)
+{
+    if (!h) return;
+    cudaFree(h->xcol);
+    cudaFree(h->codes_local);
+    cudaFree(h->codes_recv);
+    cudaFree(h->codes_own);
+    cudaFree(h->packed_own);
+    cudaFree(h->loss_all);
+    delete h;
+}
+
+rb_status rb_kmeans_dist_create(rb_comm *c, const float *x_local, size_t n_local, ptrdiff_t x_row_stride, size_t M,
+                                size_t k, size_t dsub, void *stream, rb_kmeans_dist **out)
+{
+    if (!out) return RB_ERR_INVALID;
+    *out = nullptr;
+    if (!c || (n_local && !x_local)) {
+        set_error("NULL argument");
+        return RB_ERR_INVALID;
+    }
+    if (M == 0 || k == 0 || dsub == 0 || x_row_stride < (ptrdiff_t)(M * dsub)) {
+        set_error("bad shape (M=%zu k=%zu dsub=%zu row stride %td)", M, k, dsub, x_row_stride);
+        return RB_ERR_SHAPE;
+    }
+    RB_TRY(require_nccl());
+    cudaStream_t st = (cudaStream_t)stream;
+    const int W = c->world, me = c->rank;
+    rb_kmeans_dist *h = new rb_kmeans_dist();
+    h->c = c;
+    h->M = M; h->k = k; h->dsub = dsub; h->d = M * dsub;
+    h->x_local = x_local;
+    h->ldx = x_row_stride;
+    h->n_local = n_local;
+    h->code_width = rb_kmeans_code_width(k);
+    h->m_lo.resize(W + 1);
+    for (int r = 0; r <= W; r++) h->m_lo[r] = M * (size_t)r / (size_t)W;
+    auto body = [&]() -> rb_status {
+        // row counts of every rank (rank r's rows follow rank r - 1's in the reference's row order)
+        unsigned long long *cnt_dev = nullptr;
+        RB_CUDA_TRY(cudaMalloc(&cnt_dev, (size_t)(W + 1) * sizeof(unsigned long long)));
+        const unsigned long long mine = n_local;
+        std::vector<unsigned long long> cnt(W);
+        rb_status s = [&]() -> rb_status {
+            RB_CUDA_TRY(cudaMemcpyAsync(cnt_dev + W, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+            RB_NCCL_TRY(nccl().AllGather(cnt_dev + W, cnt_dev, 1, ncclUint64, c->comm, st));
+            RB_CUDA_TRY(cudaMemcpyAsync(cnt.data(), cnt_dev, (size_t)W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            RB_CUDA_TRY(cudaStreamSynchronize(st));
+            return RB_OK;
+        }();
+        cudaFree(cnt_dev);
+        RB_TRY(s);
+        h->n_of.resize(W);
+        h->row_off.resize(W + 1);
+        h->row_off[0] = 0;
+        for (int r = 0; r < W; r++) {
+            h->n_of[r] = (size_t)cnt[r];
+            h->row_off[r + 1] = h->row_off[r] + h->n_of[r];
+        }
+        h->n_total = h->row_off[W];
+        h->pitch_local = rb_kmeans_code_pitch(n_local);
+        h->pitch_total = rb_kmeans_code_pitch(h->n_total);
+        const size_t m_own = h->m_own(), dcols = m_own * dsub, cw = (size_t)h->code_width;
+        size_t recv_bytes = 0;
+        for (int r = 0; r < W; r++) recv_bytes += m_own * rb_kmeans_code_pitch(h->n_of[r]) * cw;
+        RB_CUDA_TRY(cudaMalloc(&h->xcol, (h->n_total * dcols + 4) * sizeof(float)));
+        RB_CUDA_TRY(cudaMalloc(&h->codes_local, M * h->pitch_local * cw + 16));
+        RB_CUDA_TRY(cudaMalloc(&h->codes_recv, recv_bytes + 16));
+        RB_CUDA_TRY(cudaMalloc(&h->codes_own, m_own * h->pitch_total * cw + 16));
+        RB_CUDA_TRY(cudaMemsetAsync(h->codes_own, 0, m_own * h->pitch_total * cw + 16, st));
+        RB_CUDA_TRY(cudaMalloc(&h->packed_own, (rb_kmeans_packed_len(m_own ? m_own : 1, k, dsub)) * sizeof(float)));
+        RB_CUDA_TRY(cudaMalloc(&h->loss_all, M * sizeof(float)));
+        // one-time all-to-all of the training matrix: rank s receives x[rows of r, columns of s] from every r
+        float *sendbuf = nullptr;
+        RB_CUDA_TRY(pool_malloc((void **)&sendbuf, (n_local * h->d + 4) * sizeof(float), st));
+        rb_status s2 = [&]() -> rb_status {
+            std::vector<float *> send_at(W);
+            size_t off = 0;
+            for (int r = 0; r < W; r++) {
+                const size_t cols = (h->m_lo[r + 1] - h->m_lo[r]) * dsub;
+                send_at[r] = sendbuf + off;
+                if (cols && n_local)
+                    RB_CUDA_TRY(cudaMemcpy2DAsync(send_at[r], cols * sizeof(float), x_local + h->m_lo[r] * dsub,
+                                                  (size_t)x_row_stride * sizeof(float), cols * sizeof(float), n_local,
+                                                  cudaMemcpyDeviceToDevice, st));
+                off += n_local * cols;
+            }
+            RB_NCCL_TRY(nccl().GroupStart());
+            for (int r = 0; r < W; r++) {
+                const size_t cols_r = (h->m_lo[r + 1] - h->m_lo[r]) * dsub;
+                if (n_local * cols_r) RB_NCCL_TRY(nccl().Send(send_at[r], n_local * cols_r, ncclFloat, r, c->comm, st));
+                if (h->n_of[r] * dcols)
+                    RB_NCCL_TRY(nccl().Recv(h->xcol + h->row_off[r] * dcols, h->n_of[r] * dcols, ncclFloat, r, c->comm, st));
+            }
+            RB_NCCL_TRY(nccl().GroupEnd());
+            return RB_OK;
+        }();
+        cudaFreeAsync(sendbuf, st);
+        return s2;
+    };
+    (void)me;
+    const rb_status s = body();
+    if (s != RB_OK) {
+        rb_kmeans_dist_destroy(h);
+        return s;
+    }
+    *out = h;
+    return RB_OK;
+}
+
+rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *h, float *centroids, float *loss_or_null, void *stream)
+{
+    if (!h || !centroids) {
+        set_error("NULL argument");
+        return RB_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    rb_comm *c = h->c;
+    const int W = c->world, me = c->rank;
+    const size_t M = h->M, k = h->k, dsub = h->dsub, cw = (size_t)h->code_width;
+    const size_t m_own = h->m_own(), dcols = m_own * dsub;
+    // 1. cluster_assignments of the local rows against all M codebooks (kmeans.rs:319)
+    RB_TRY(rb_kmeans_assign(h->x_local, h->n_local, h->ldx, centroids, M, k, dsub, h->codes_local, stream));
+    // 2. the assignments of subquantizers [m_lo[s], m_lo[s+1]) go to rank s (column-major blocks are contiguous)
+    std::vector<unsigned char *> recv_at(W);
+    {
+        size_t off = 0;
+        for (int r = 0; r < W; r++) {
+            recv_at[r] = h->codes_recv + off;
+            off += m_own * rb_kmeans_code_pitch(h->n_of[r]) * cw;
+        }
+    }
+    RB_NCCL_TRY(nccl().GroupStart());
+    for (int r = 0; r < W; r++) {
+        const size_t send_bytes = (h->m_lo[r + 1] - h->m_lo[r]) * h->pitch_local * cw;
+        const size_t recv_bytes = m_own * rb_kmeans_code_pitch(h->n_of[r]) * cw;
+        if (send_bytes && h->n_local)
+            RB_NCCL_TRY(nccl().Send(h->codes_local + h->m_lo[r] * h->pitch_local * cw, send_bytes, ncclUint8, r, c->comm, st));
+        if (recv_bytes && h->n_of[r]) RB_NCCL_TRY(nccl().Recv(recv_at[r], recv_bytes, ncclUint8, r, c->comm, st));
+    }
+    RB_NCCL_TRY(nccl().GroupEnd());
+    // rows of all ranks in rank order = the reference's row order: [m_own][pitch_total]
+    for (int r = 0; r < W; r++)
+        if (m_own && h->n_of[r])
+            RB_CUDA_TRY(cudaMemcpy2DAsync(h->codes_own + h->row_off[r] * cw, h->pitch_total * cw, recv_at[r],
+                                          rb_kmeans_code_pitch(h->n_of[r]) * cw, h->n_of[r] * cw, m_own,
+                                          cudaMemcpyDeviceToDevice, st));
+    // 3. update_centroids of the owned subquantizers over ALL rows, in row order (kmeans.rs:166-198)
+    if (m_own) {
+        RB_TRY(launch_kmeans_accumulate(h->xcol, h->n_total, (ptrdiff_t)dcols, cw == 1 ? h->codes_own : nullptr,
+                                        cw == 4 ? reinterpret_cast<const uint32_t *>(h->codes_own) : nullptr, h->pitch_total,
+                                        m_own, k, dsub, nullptr, h->packed_own, 1, st));
+        RB_TRY(launch_kmeans_finalize(h->packed_own, m_own, k, dsub, h->n_total, centroids + h->m_lo[me] * k * dsub,
+                                      h->loss_all + h->m_lo[me], st));
+    }
+    // 4. everyone gets everyone's new centroids (and losses)
+    RB_NCCL_TRY(nccl().GroupStart());
+    for (int r = 0; r < W; r++) {
+        const size_t mr = h->m_lo[r + 1] - h->m_lo[r];
+        if (!mr) continue;
+        float *cen_r = centroids + h->m_lo[r] * k * dsub;
+        RB_NCCL_TRY(nccl().Broadcast(cen_r, cen_r, mr * k * dsub, ncclFloat, r, c->comm, st));
+        RB_NCCL_TRY(nccl().Broadcast(h->loss_all + h->m_lo[r], h->loss_all + h->m_lo[r], mr, ncclFloat, r, c->comm, st));
+    }
+    RB_NCCL_TRY(nccl().GroupEnd());
+    if (loss_or_null)
+        RB_CUDA_TRY(cudaMemcpyAsync(loss_or_null, h->loss_all, M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return RB_OK;
+}
+
+rb_status rb_pq_train_dist(rb_comm *c, const float *instances_local, size_t n_local, size_t n_total, size_t d,
+                           ptrdiff_t row_stride, size_t n_subquantizers, uint32_t n_subquantizer_bits, size_t n_iterations,
+                           size_t n_attempts, const float *initial_centroids, float *loss_out, int mem_kind, void *stream,
+                           rb_pq **out)
+{
+    if (!out) return RB_ERR_INVALID;
+    *out = nullptr;
+    const size_t M = n_subquantizers;
+    RB_TRY(rb_check_quantizer_invariants(M, n_subquantizer_bits, n_iterations, n_attempts, n_total, d, nullptr));  // pq.rs:213-219
+    if (!c || !initial_centroids || (n_local && !instances_local)) {
+        set_error("NULL argument");
+        return RB_ERR_INVALID;
+    }
+    const size_t k = (size_t)1 << n_subquantizer_bits;
+    if (k >= n_total) {  // kmeans.rs:62-67
+        set_error("Cannot pick more centroids than instances: %zu instances, %zu centroids", n_total, k);
+        return RB_ERR_K_MEANS_K;
+    }
+    if (row_stride < (ptrdiff_t)d) {
+        set_error("row stride %td < %zu columns", row_stride, d);
+        return RB_ERR_SHAPE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t dsub = d / M, qn = M * k * dsub;
+    float *xdev = nullptr;
+    const float *x = instances_local;
+    ptrdiff_t ldx = row_stride;
+    if (mem_kind == RB_MEM_HOST) {
+        RB_CUDA_TRY(cudaMalloc(&xdev, (n_local * d + 4) * sizeof(float)));
+        if (n_local)
+            RB_CUDA_TRY(cudaMemcpy2DAsync(xdev, d * sizeof(float), instances_local, (size_t)row_stride * sizeof(float),
+                                          d * sizeof(float), n_local, cudaMemcpyHostToDevice, st));
+        x = xdev;
+        ldx = (ptrdiff_t)d;
+    }
+    rb_kmeans_dist *h = nullptr;
+    float *cen = nullptr, *loss_dev = nullptr;
+    std::vector<float> best_q(qn), cand_q(qn), best_loss(M, 0.f), cand_loss(M, 0.f);
+    auto body = [&]() -> rb_status {
+        RB_TRY(rb_kmeans_dist_create(c, x, n_local, ldx, M, k, dsub, stream, &h));
+        if (h->n_total != n_total) {
+            set_error("the ranks hold %zu rows in total, n_total says %zu", h->n_total, n_total);
+            return RB_ERR_SHAPE;
+        }
+        RB_CUDA_TRY(cudaMalloc(&cen, qn * sizeof(float)));
+        RB_CUDA_TRY(cudaMalloc(&loss_dev, M * sizeof(float)));
+        for (size_t a = 0; a < n_attempts; a++) {  // pq.rs:168-183, all subquantizers advance together
+            RB_CUDA_TRY(cudaMemcpyAsync(cen, initial_centroids + a * qn, qn * sizeof(float), cudaMemcpyHostToDevice, st));
+            for (size_t it = 0; it < n_iterations; it++)  // kmeans.rs:279-284
+                RB_TRY(rb_kmeans_dist_iterate(h, cen, it + 1 == n_iterations ? loss_dev : nullptr, stream));
+            RB_CUDA_TRY(cudaMemcpyAsync(cand_q.data(), cen, qn * sizeof(float), cudaMemcpyDeviceToHost, st));
+            RB_CUDA_TRY(cudaMemcpyAsync(cand_loss.data(), loss_dev, M * sizeof(float), cudaMemcpyDeviceToHost, st));
+            RB_CUDA_TRY(cudaStreamSynchronize(st));
+            for (size_t m = 0; m < M; m++) {  // pq.rs:184-187: min_by_key(OrderedFloat(loss)) keeps the first minimum
+                const float l = cand_loss[m], b = best_loss[m];
+                const bool less = (l < b) || ((b != b) && (l == l));
+                if (a == 0 || less) {
+                    best_loss[m] = l;
+                    memcpy(best_q.data() + m * k * dsub, cand_q.data() + m * k * dsub, k * dsub * sizeof(float));
+                }
+            }
+        }
+        return RB_OK;
+    };
+    const rb_status s = body();
+    rb_kmeans_dist_destroy(h);
+    cudaFree(cen);
+    cudaFree(loss_dev);
+    cudaFree(xdev);
+    RB_TRY(s);
+    if (loss_out) memcpy(loss_out, best_loss.data(), M * sizeof(float));
+    return rb_pq_create(best_q.data(), M, k, dsub, nullptr, out);
+}
+
+// One process, several GPUs: one host thread per device, communicators from ncclCommInitAll, each thread runs the
+// rank's part of rb_pq_train_dist on its contiguous block of rows.  instances: HOST [n, d].
+rb_status rb_pq_train_multi(const int *devices, int n_devices, const float *instances, size_t n, size_t d,
+                            ptrdiff_t row_stride, size_t n_subquantizers, uint32_t n_subquantizer_bits, size_t n_iterations,
+                            size_t n_attempts, const float *initial_centroids, float *loss_out, rb_pq **out)
+{
+    if (!out) return RB_ERR_INVALID;
+    *out = nullptr;
+    if (!devices || n_devices <= 0 || !instances || !initial_centroids) {
+        set_error("NULL argument / no devices");
+        return RB_ERR_INVALID;
+    }
+    RB_TRY(rb_check_quantizer_invariants(n_subquantizers, n_subquantizer_bits, n_iterations, n_attempts, n, d, nullptr));
+    RB_TRY(require_nccl());
+    const int W = n_devices;
+    std::vector<ncclComm_t> comms(W);
+    RB_NCCL_TRY(nccl().CommInitAll(comms.data(), W, devices));
+    std::vector<rb_status> status(W, RB_OK);
+    std::vector<std::string> errors(W);
+    std::vector<rb_pq *> pqs(W, nullptr);
+    std::vector<std::vector<float>> losses(W, std::vector<float>(n_subquantizers));
+    const size_t per = (n + (size_t)W - 1) / (size_t)W;
+    std::vector<std::thread> threads;
+    for (int r = 0; r < W; r++) {
+        threads.emplace_back([&, r]() {
+            rb_comm c;
+            c.comm = comms[r];
+            c.rank = r;
+            c.world = W;
+            c.device = devices[r];
+            if (cudaSetDevice(devices[r]) != cudaSuccess) {
+                status[r] = RB_ERR_CUDA;
+                errors[r] = "cudaSetDevice failed";
+                return;
+            }
+            const size_t lo = per * (size_t)r < n ? per * (size_t)r : n;
+            const size_t hi = lo + per < n ? lo + per : n;
+            cudaStream_t st = nullptr;
+            cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+            status[r] = rb_pq_train_dist(&c, instances + (ptrdiff_t)lo * row_stride, hi - lo, n, d, row_stride, n_subquantizers,
+                                         n_subquantizer_bits, n_iterations, n_attempts, initial_centroids, losses[r].data(),
+                                         RB_MEM_HOST, st, &pqs[r]);
+            if (status[r] != RB_OK) errors[r] = rb_last_error_message();
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        });
+    }
+    for (auto &t : threads) t.join();
+    for (int r = 0; r < W; r++) nccl().CommDestroy(comms[r]);
+    rb_status s = RB_OK;
+    for (int r = 0; r < W; r++)
+        if (status[r] != RB_OK && s == RB_OK) {
+            s = status[r];
+            set_error("device %d: %s", devices[r], errors[r].c_str());
+        }
+    // every rank holds the same quantizer: keep the first device's handle
+    for (int r = 1; r < W; r++) {
+        if (pqs[r]) {
+            cudaSetDevice(devices[r]);
+            rb_pq_destroy(pqs[r]);
+        }
+    }
+    cudaSetDevice(devices[0]);
+    if (s != RB_OK) {
+        if (pqs[0]) rb_pq_destroy(pqs[0]);
+        return s;
+    }
+    if (loss_out) memcpy(loss_out, losses[0].data(), n_subquantizers * sizeof(float));
+    *out = pqs[0];
+    return RB_OK;
+}
+
+}  // extern "C"

@@ -85,6 +85,100 @@ def slice_len(m0: int, m1: int, k: int, dsub: int) -> int:
     return (m1 - m0) * (k * dsub + k + 1)
 
 
+class Comm:
+    """One rank of an NCCL communicator owned by the CUDA library (rb_comm).  The 128-byte NCCL id is created on
+    rank 0 and handed to the other ranks through `torch.distributed` (any backend) -- plumbing only: every exchange
+    of the training loop itself is issued from C++ (csrc/dist.cu)."""
+
+    def __init__(self, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        if rank is None:
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = torch.zeros((128,), dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            check(lib.rb_comm_unique_id(buf, 128))
+            ident = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        if world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else None
+            t = ident.to(dev) if dev is not None else ident
+            dist.broadcast(t, src=dist.get_process_group_ranks(group)[0] if group is not None else 0, group=group)
+            ident = t.cpu()
+        self.rank, self.world = rank, world
+        self._h = C.c_void_p()
+        raw = (C.c_ubyte * 128).from_buffer_copy(ident.numpy().tobytes())
+        check(lib.rb_comm_create(raw, rank, world, C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self) -> None:
+        if self._h:
+            lib.rb_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+def subquantizer_range(M: int, rank: int, world: int) -> Tuple[int, int]:
+    """Subquantizers whose centroid update `rank` owns in the sharded k-means (rb_dist_subquantizer_range)."""
+    import ctypes as C
+
+    a, b = C.c_size_t(), C.c_size_t()
+    check(lib.rb_dist_subquantizer_range(M, rank, world, C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
+
+
+class ShardedKMeans:
+    """Data-parallel Pq k-means with rows sharded over the ranks of `comm` (rb_kmeans_dist): assignment is sharded by
+    rows, the ordered centroid update by subquantizers, so the result is bit-identical to a one-GPU run for any
+    number of GPUs (src/kmeans.rs:185-189 adds every cluster's rows sequentially in row order).  `x_local` is this
+    rank's block of rows (rank r's rows follow rank r-1's) and must stay alive and unchanged."""
+
+    def __init__(self, comm: Comm, x_local, M: int, k: int, dsub: int):
+        import ctypes as C
+
+        import torch
+
+        assert x_local.is_cuda and x_local.dtype == torch.float32 and x_local.stride(1) == 1
+        self.comm, self.x_local, self.shape = comm, x_local, (M, k, dsub)
+        self._h = C.c_void_p()
+        check(lib.rb_kmeans_dist_create(comm.handle, x_local.data_ptr(), x_local.shape[0], x_local.stride(0), M, k, dsub,
+                                        torch.cuda.current_stream().cuda_stream, C.byref(self._h)))
+
+    def iterate(self, centroids, loss=None) -> None:
+        """One kmeans_iteration (src/kmeans.rs:308-327) in place on `centroids` [M,k,dsub] (device, identical on
+        every rank); `loss`: optional device [M]."""
+        import torch
+
+        assert tuple(centroids.shape) == self.shape and centroids.is_contiguous()
+        check(lib.rb_kmeans_dist_iterate(self._h, centroids.data_ptr(), None if loss is None else loss.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+
+    def close(self) -> None:
+        if self._h:
+            import torch
+
+            torch.cuda.synchronize()
+            lib.rb_kmeans_dist_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def kmeans_data_parallel(x_local, n_total: int, centroids, n_iterations: int, group=None,
                          local_step: Optional[Callable] = None, finalize: Optional[Callable] = None,
                          on_iteration: Optional[Callable] = None, mode: str = "allreduce",
