@@ -243,43 +243,89 @@ def run_ours(args) -> None:
         "roofline": {"bound": "hbm", "achieved": rec_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": rec_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_vector": M + 4 * D}}
     del rec
-    # C3: Pq k-means 1M x 768, 96 x 256, rows sharded over the ranks (strong scaling), one all-reduce per iteration
-    from reductive_b200.dist import kmeans_data_parallel, shard_rows
+    # C3: Pq k-means 1M x 768, 96 x 256 centroids, 25 iterations; rows sharded over the ranks (strong scaling).
+    # Sharded mode (csrc/dist.cu): assignment by rows, ordered centroid update by subquantizers, NCCL from the C++
+    # library -- bit-identical to a one-GPU run, which is MEASURED below against a one-GPU run of the same rows.
+    from reductive_b200.dist import Comm, ShardedKMeans, cuda_finalize, cuda_local_step, shard_rows
 
-    n3, M3, dsub3, iters3 = 1_000_000, 96, 8, 5
+    n3, M3, dsub3, iters3 = 1_000_000, 96, 8, 25
+
+    def block3(r):
+        a, b = shard_rows(n3, r, world)
+        gb = torch.Generator(device=dev)
+        gb.manual_seed(77 + r)
+        return torch.randn((b - a, M3 * dsub3), generator=gb, device=dev, dtype=torch.float32)
+
     lo, hi = shard_rows(n3, rank, world)
-    g3 = torch.Generator(device=dev)
-    g3.manual_seed(77 + rank)
-    x3 = torch.randn((hi - lo, M3 * dsub3), generator=g3, device=dev, dtype=torch.float32)
-    gi = torch.Generator(device=dev)
-    gi.manual_seed(5)
-    cen3 = torch.randn((M3, K_CENTROIDS, dsub3), generator=gi, device=dev, dtype=torch.float32)
-    kmeans_data_parallel(x3, n3, cen3, 2)
+    x3 = block3(rank)
+    # initial centroid (m, j) = row (7919 j + 104729 m) mod n of the training matrix, columns of m
+    jj = torch.arange(K_CENTROIDS, device=dev).view(1, -1)
+    mm = torch.arange(M3, device=dev).view(-1, 1)
+    rows0 = (7919 * jj + 104729 * mm) % n3                                   # [M, k]
+    mine = (rows0 >= lo) & (rows0 < hi)
+    cen0 = torch.zeros((M3, K_CENTROIDS, dsub3), device=dev, dtype=torch.float32)
+    cols = (mm * dsub3).unsqueeze(-1) + torch.arange(dsub3, device=dev).view(1, 1, -1)  # [M, 1, dsub]
+    picked = x3[(rows0 - lo).clamp(0, hi - lo - 1).unsqueeze(-1), cols.expand(M3, K_CENTROIDS, dsub3)]
+    cen0[mine] = picked[mine]
+    if world > 1:
+        dist.all_reduce(cen0, op=dist.ReduceOp.SUM)  # every entry comes from exactly one rank: exact
+    loss3 = torch.zeros((M3,), device=dev)
+    if world > 1:
+        comm = Comm()
+        km = ShardedKMeans(comm, x3, M3, K_CENTROIDS, dsub3)
+        step3 = lambda c, l=None: km.iterate(c, l)  # noqa: E731
+    else:
+        packed3 = torch.empty((M3 * K_CENTROIDS * dsub3 + M3 * K_CENTROIDS + M3,), device=dev)
+
+        def step3(c, l=None):
+            cuda_local_step(x3, c, packed3)
+            cuda_finalize(packed3, n3, c, l)
+    cen3 = cen0.clone()
+    for _ in range(2):
+        step3(cen3)
+    cen3 = cen0.clone()
     barrier()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record(stream)
-    kmeans_data_parallel(x3, n3, cen3, iters3)
+    for it in range(iters3):
+        step3(cen3, loss3 if it + 1 == iters3 else None)
     k1.record(stream)
     barrier()
     tk = torch.tensor([k0.elapsed_time(k1) / iters3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tk, op=dist.ReduceOp.MAX)
-    extra["pq_kmeans"] = {"workload": f"C3: 1M x 768 f32, 96 x 256 centroids, rows sharded over {world} GPU(s)",
-                          "sec_per_iter": float(tk.item()) * 1e-3, "iters_timed": iters3, "mode": "allreduce",
-                          "allreduce_bytes_per_iter": 4 * (M3 * K_CENTROIDS * (dsub3 + 1) + M3) if world > 1 else 0,
-                          "parity": "bit-identical to the oracle on 1 GPU; with >1 GPU the all-reduce changes the "
-                                    "summation order (centroids drift ~1e-3 after 10 iterations, loss ~1e-6)"}
-    if world > 1:  # chained mode: running sums relayed rank to rank, bit-identical to a one-GPU run
-        kmeans_data_parallel(x3, n3, cen3, 1, mode="chained")
-        barrier()
-        k0.record(stream)
-        kmeans_data_parallel(x3, n3, cen3, iters3, mode="chained")
-        k1.record(stream)
-        barrier()
-        tk = torch.tensor([k0.elapsed_time(k1) / iters3], device=dev, dtype=torch.float64)
-        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
-        extra["pq_kmeans_chained"] = {"sec_per_iter": float(tk.item()) * 1e-3, "iters_timed": iters3,
-                                      "parity": "bit-identical to the one-GPU run and the oracle"}
+    it_ms = float(tk.item())
+    # one pass of assignment + one pass of the update read x twice: 2 * 4 * d bytes per row + the codes (written, read)
+    it_bytes = n3 * (2 * 4 * M3 * dsub3 + 2 * M3)
+    it_gbs = it_bytes / (it_ms * 1e-3) / 1e9 / world
+    bit_identical = None
+    if world > 1:
+        km.close()
+        same_everywhere = cen3.view(torch.int32).clone()
+        dist.broadcast(same_everywhere, src=0)
+        agree = torch.tensor([int(torch.equal(same_everywhere, cen3.view(torch.int32)))], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if rank == 0:  # the one-GPU run of the same rows
+            x_all = torch.cat([block3(r) for r in range(world)])
+            ref = cen0.clone()
+            packed3 = torch.empty((M3 * K_CENTROIDS * dsub3 + M3 * K_CENTROIDS + M3,), device=dev)
+            for _ in range(iters3):
+                cuda_local_step(x_all, ref, packed3)
+                cuda_finalize(packed3, n3, ref, None)
+            bit_identical = bool(torch.equal(ref.view(torch.int32), cen3.view(torch.int32))) and bool(agree.item())
+            del x_all
+        comm.close()
+    extra["pq_kmeans"] = {
+        "workload": f"C3: Pq k-means 1M x 768 f32, 96 x 256 centroids, {iters3} iterations from SURVEY 8d's row picks, "
+                    f"rows sharded over {world} GPU(s)",
+        "sec_per_iter": it_ms * 1e-3, "iters_timed": iters3,
+        "mode": "sharded: assignment by rows, ordered update by subquantizers (NCCL inside the C++ library)" if world > 1
+                else "one GPU: assignment + ordered update (reference summation order)",
+        "bit_identical_to_1gpu": bit_identical if world > 1 else True,
+        "exchange_bytes_per_iter": (n3 * M3 + 4 * M3 * K_CENTROIDS * dsub3 * world) if world > 1 else 0,
+        "roofline": {"bound": "hbm", "achieved": it_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s per GPU",
+                     "frac": it_gbs / peaks["hbm_gbs"],
+                     "algorithmic_bytes_per_iter": it_bytes, "note": "two passes over x (assign, update) + codes"}}
     del x3
 
     # C5: one 12.5M x 128 shard per GPU (100M rows over 8 GPUs), M = 16; device-generated, no collective
@@ -299,8 +345,11 @@ def run_ours(args) -> None:
     t5 = torch.tensor([k0.elapsed_time(k1) / 3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+    c5_gbs = n5 * (4 * M5 * dsub5 + M5) / (float(t5.item()) * 1e-3) / 1e9
     extra["c5_streaming_shard"] = {"workload": f"C5: quantize_batch 12.5M x 128 per GPU x {world} GPU(s), 16 x 256 centroids",
-                                   "ms": float(t5.item()), "vectors_per_s": world * n5 / (float(t5.item()) * 1e-3)}
+                                   "ms": float(t5.item()), "vectors_per_s": world * n5 / (float(t5.item()) * 1e-3),
+                                   "roofline": {"bound": "hbm", "achieved": c5_gbs, "peak": peaks["hbm_gbs"],
+                                                "unit": "GB/s per GPU", "frac": c5_gbs / peaks["hbm_gbs"]}}
     del x5, c5
     # C4: projected (Opq / GaussianOpq) encode + decode, 1M x 300, M = 30; exact-order FP32 rotation + encode / gather
     n4 = 1_000_000
@@ -323,7 +372,12 @@ def run_ours(args) -> None:
     barrier()
     extra["c4_projected"] = {"workload": "C4: 1M x 300 with a 300 x 300 projection, M = 30 (per GPU); rotation on tcgen05 "
                                          "(project_tc.cu): codes bit-exact, rotated reconstruction within 1e-5",
-                             "encode_ms": e4, "decode_ms": k0.elapsed_time(k1)}
+                             "encode_ms": e4, "decode_ms": k0.elapsed_time(k1),
+                             "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                                          "encode_achieved": n4 * (4 * D + M) / (e4 * 1e-3) / 1e9,
+                                          "encode_frac": n4 * (4 * D + M) / (e4 * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                          "decode_achieved": n4 * (4 * D + M) / (k0.elapsed_time(k1) * 1e-3) / 1e9,
+                                          "decode_frac": n4 * (4 * D + M) / (k0.elapsed_time(k1) * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     del rec4, c4
 
     if rank == 0:

@@ -330,16 +330,24 @@ rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *h, float *centroids, float *los
         RB_TRY(launch_kmeans_finalize(h->packed_own, m_own, k, dsub, h->n_total, centroids + h->m_lo[me] * k * dsub,
                                       h->loss_all + h->m_lo[me], st));
     }
-    // 4. everyone gets everyone's new centroids (and losses)
-    RB_NCCL_TRY(nccl().GroupStart());
-    for (int r = 0; r < W; r++) {
-        const size_t mr = h->m_lo[r + 1] - h->m_lo[r];
-        if (!mr) continue;
-        float *cen_r = centroids + h->m_lo[r] * k * dsub;
-        RB_NCCL_TRY(nccl().Broadcast(cen_r, cen_r, mr * k * dsub, ncclFloat, r, c->comm, st));
-        RB_NCCL_TRY(nccl().Broadcast(h->loss_all + h->m_lo[r], h->loss_all + h->m_lo[r], mr, ncclFloat, r, c->comm, st));
+    // 4. everyone gets everyone's new centroids (and, when asked for, losses): one in-place all-gather when the
+    //    subquantizers divide evenly, else one broadcast per rank
+    const bool even = M % (size_t)W == 0;
+    if (even) {
+        RB_NCCL_TRY(nccl().AllGather(centroids + h->m_lo[me] * k * dsub, centroids, m_own * k * dsub, ncclFloat, c->comm, st));
+        if (loss_or_null) RB_NCCL_TRY(nccl().AllGather(h->loss_all + h->m_lo[me], h->loss_all, m_own, ncclFloat, c->comm, st));
+    } else {
+        RB_NCCL_TRY(nccl().GroupStart());
+        for (int r = 0; r < W; r++) {
+            const size_t mr = h->m_lo[r + 1] - h->m_lo[r];
+            if (!mr) continue;
+            float *cen_r = centroids + h->m_lo[r] * k * dsub;
+            RB_NCCL_TRY(nccl().Broadcast(cen_r, cen_r, mr * k * dsub, ncclFloat, r, c->comm, st));
+            if (loss_or_null)
+                RB_NCCL_TRY(nccl().Broadcast(h->loss_all + h->m_lo[r], h->loss_all + h->m_lo[r], mr, ncclFloat, r, c->comm, st));
+        }
+        RB_NCCL_TRY(nccl().GroupEnd());
     }
-    RB_NCCL_TRY(nccl().GroupEnd());
     if (loss_or_null)
         RB_CUDA_TRY(cudaMemcpyAsync(loss_or_null, h->loss_all, M * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return RB_OK;

@@ -382,7 +382,7 @@ __device__ __forceinline__ float ldg_l2_128(const float *p)
     return v;
 }
 
-template <int DSUB>
+template <int DSUB, int UN>
 __global__ void __launch_bounds__(256)
 ordered_chain_kernel(const float *__restrict__ x, long long ldx, int M, int k, int n_chunks, int chunk, int kChunkRows,
                      const uint16_t *__restrict__ list, const uint32_t *__restrict__ lstart,
@@ -391,10 +391,8 @@ ordered_chain_kernel(const float *__restrict__ x, long long ldx, int M, int k, i
     // lanes = (chain c, component t): a warp carries 32 / DSUB independent chains, i.e. clusters; every lane walks
     // its own cluster's rows of this chunk in order, so the reference's sequential adds need no cross-lane traffic
     constexpr int CH = 32 / DSUB;  // chains per warp
-#ifndef RB_CHAIN_UN
-#define RB_CHAIN_UN 8
-#endif
-    constexpr int UN = RB_CHAIN_UN;  // rows in flight per chain
+    // UN = rows in flight per chain: 8 when the GPU carries many chains (a whole training matrix), 32 when it carries
+    // few (the subquantizer shard of a multi-GPU run: a launch is then bound by the latency of its batches)
     const int lane = threadIdx.x & 31;
     const int c = lane / DSUB, t = lane % DSUB;
     const long long total_mj = (long long)M * k;
@@ -497,11 +495,16 @@ rb_status launch_ordered_fast(const float *x, size_t n, ptrdiff_t ldx, const uin
                                         cudaMemcpyDeviceToDevice, stream));
         }
         const unsigned blocks = (unsigned)ceil_div(ceil_div(M * k, 32 / dsub), 8);
+        const bool deep = M * k * dsub <= (size_t)sm_count() * 512;  // fewer than ~16 chain warps per SM
         for (size_t c = 0; c < n_chunks; c++) {
 #define RB_CHAIN(D)                                                                                                  \
     case D:                                                                                                          \
-        ordered_chain_kernel<D><<<blocks, 256, 0, stream>>>(x, (long long)ldx, (int)M, (int)k, (int)n_chunks, (int)c, \
-                                                            kChunkRows, list, lstart, init, packed);                             \
+        if (deep)                                                                                                    \
+            ordered_chain_kernel<D, 32><<<blocks, 256, 0, stream>>>(x, (long long)ldx, (int)M, (int)k, (int)n_chunks, \
+                                                                    (int)c, kChunkRows, list, lstart, init, packed);  \
+        else                                                                                                         \
+            ordered_chain_kernel<D, 8><<<blocks, 256, 0, stream>>>(x, (long long)ldx, (int)M, (int)k, (int)n_chunks,  \
+                                                                   (int)c, kChunkRows, list, lstart, init, packed);   \
         break;
             switch (dsub) {
                 RB_CHAIN(1) RB_CHAIN(2) RB_CHAIN(3) RB_CHAIN(4) RB_CHAIN(5) RB_CHAIN(6) RB_CHAIN(8) RB_CHAIN(10)

@@ -12,7 +12,7 @@ current device, any strides); the index type `I` becomes a numpy integer dtype. 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -237,9 +237,12 @@ class Pq(QuantizeVector, Reconstruct, TrainPq):
     # ---- TrainPq (pq.rs:196-250) ------------------------------------------------------------------
     @classmethod
     def train_pq_using(cls, n_subquantizers, n_subquantizer_bits, n_iterations, n_attempts, instances, rng,
-                       initial_centroids: Optional[np.ndarray] = None, return_loss: bool = False):
+                       initial_centroids: Optional[np.ndarray] = None, return_loss: bool = False,
+                       devices: Optional[Sequence[int]] = None):
         """`initial_centroids` ([n_attempts, M, k, dsub]) overrides the random instance draw — the hook the
-        parity tests use to start the CUDA path and the oracle from identical centroids."""
+        parity tests use to start the CUDA path and the oracle from identical centroids.  `devices` (host
+        instances only): train on several GPUs from this one process (rb_pq_train_multi: rows split into contiguous
+        blocks, bit-identical to the one-GPU result); the quantizer lives on devices[0]."""
         x = _Arr(instances, want_float=True)
         if len(x.shape) != 2:
             raise ReductivePanic("instances must be a matrix")
@@ -264,6 +267,14 @@ class Pq(QuantizeVector, Reconstruct, TrainPq):
             init = np.ascontiguousarray(initial_centroids, np.float32).reshape(n_attempts, M, k, dsub)
         loss = np.zeros((M,), np.float32)
         h = C.c_void_p()
+        if devices is not None and len(devices) > 1:
+            if x.mem != MEM_HOST or x.strides[1] != 1:
+                raise ValueError("multi-device training takes host instances with unit column stride")
+            dev = (C.c_int * len(devices))(*[int(v) for v in devices])
+            check(lib.rb_pq_train_multi(dev, len(devices), x.ptr, n, d, x.strides[0], M, n_subquantizer_bits,
+                                        n_iterations, n_attempts, init.ctypes.data, loss.ctypes.data, C.byref(h)))
+            pq = cls._from_handle(h)
+            return (pq, loss) if return_loss else pq
         check(lib.rb_pq_train(x.ptr, n, d, x.strides[0], x.strides[1], M, n_subquantizer_bits, n_iterations,
                               n_attempts, init.ctypes.data, loss.ctypes.data, x.mem, x.stream, C.byref(h)))
         pq = cls._from_handle(h)

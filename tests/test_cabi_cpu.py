@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_cabi.EXPORTED_SYMBOLS) == declared
     for name in declared:
         assert hasattr(_cabi.lib, name), f"{name} is declared in include/reductive_b200.h but not exported"
-    assert _cabi.lib.rb_abi_version() == 1
+    assert _cabi.lib.rb_abi_version() == 2
 
 
 def test_check_quantizer_invariants_matches_oracle(oracle):
@@ -121,3 +121,38 @@ def test_shard_rows_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
                 assert a1 == b0 and a0 <= a1
+
+
+def test_subquantizer_ranges_partition_the_subquantizers():
+    """rb_dist_subquantizer_range (host only): the ranks' ranges are contiguous, disjoint, cover [0, M), differ in
+    size by at most one, and ranks beyond M own nothing."""
+    from reductive_b200.dist import subquantizer_range
+
+    for M in (1, 2, 5, 16, 30, 96, 97):
+        for world in (1, 2, 3, 4, 8, 16):
+            end = 0
+            sizes = []
+            for r in range(world):
+                a, b = subquantizer_range(M, r, world)
+                assert a == end and b >= a
+                end = b
+                sizes.append(b - a)
+            assert end == M and max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        subquantizer_range(8, 3, 3)
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_a_device():
+    """No CPU fallback: the communicator needs NCCL + a device, training on a device list needs the devices."""
+    import ctypes as C
+
+    import torch
+
+    from reductive_b200._cabi import CudaError, check, lib
+
+    if torch.cuda.is_available():
+        pytest.skip("box has a GPU")
+    ident = (C.c_ubyte * 128)()
+    h = C.c_void_p()
+    with pytest.raises(CudaError):
+        check(lib.rb_comm_create(ident, 0, 1, C.byref(h)))
