@@ -159,6 +159,11 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def log(msg):  # progress on stderr (RB_BENCH_VERBOSE=1): where a multi-rank run stands
+        if os.environ.get("RB_BENCH_VERBOSE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    log("start")
     peaks = _peaks()
     q = _codebook()
     pq = rb.Pq(None, q)
@@ -195,6 +200,7 @@ def run_ours(args) -> None:
     ms_per_step = float(t.item()) / args.steps
     value = world * N_ROWS / (ms_per_step * 1e-3)
 
+    log("device-resident steps done")
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region -------
     # The staging buffers are allocated and driven from the CPUs NVML reports as local to this rank's GPU (NUMA
     # placement of the pinned pages matters once several ranks copy at the same time); restored afterwards.
@@ -220,6 +226,7 @@ def run_ours(args) -> None:
     if prev_affinity:
         os.sched_setaffinity(0, prev_affinity)
 
+    log("e2e done")
     # ---- secondary measurements (same JSON line, "extra"): reconstruct_batch and Pq k-means sec/iter ------
     extra = {}
     rec = torch.empty((N_ROWS, D), dtype=torch.float32, device=dev)
@@ -243,6 +250,7 @@ def run_ours(args) -> None:
         "roofline": {"bound": "hbm", "achieved": rec_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": rec_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_vector": M + 4 * D}}
     del rec
+    log("reconstruct done")
     # C3: Pq k-means 1M x 768, 96 x 256 centroids, 25 iterations; rows sharded over the ranks (strong scaling).
     # Sharded mode (csrc/dist.cu): assignment by rows, ordered centroid update by subquantizers, NCCL from the C++
     # library -- bit-identical to a one-GPU run, which is MEASURED below against a one-GPU run of the same rows.
@@ -270,9 +278,20 @@ def run_ours(args) -> None:
     if world > 1:
         dist.all_reduce(cen0, op=dist.ReduceOp.SUM)  # every entry comes from exactly one rank: exact
     loss3 = torch.zeros((M3,), device=dev)
+    log("k-means: initial centroids ready")
     if world > 1:
-        comm = Comm()
-        km = ShardedKMeans(comm, x3, M3, K_CENTROIDS, dsub3)
+        # NCCL may print its version banner on stdout when the library's communicator comes up: keep stdout for the
+        # one JSON line (file descriptor 1 points at stderr while the communicator is created)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            comm = Comm()
+            km = ShardedKMeans(comm, x3, M3, K_CENTROIDS, dsub3)
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         step3 = lambda c, l=None: km.iterate(c, l)  # noqa: E731
     else:
         packed3 = torch.empty((M3 * K_CENTROIDS * dsub3 + M3 * K_CENTROIDS + M3,), device=dev)
@@ -295,6 +314,7 @@ def run_ours(args) -> None:
     if world > 1:
         dist.all_reduce(tk, op=dist.ReduceOp.MAX)
     it_ms = float(tk.item())
+    log(f"k-means timed: {it_ms:.3f} ms/iter")
     # one pass of assignment + one pass of the update read x twice: 2 * 4 * d bytes per row + the codes (written, read)
     it_bytes = n3 * (2 * 4 * M3 * dsub3 + 2 * M3)
     it_gbs = it_bytes / (it_ms * 1e-3) / 1e9 / world
@@ -314,6 +334,7 @@ def run_ours(args) -> None:
                 cuda_finalize(packed3, n3, ref, None)
             bit_identical = bool(torch.equal(ref.view(torch.int32), cen3.view(torch.int32))) and bool(agree.item())
             del x_all
+        barrier()  # every rank is done with the communicator before any rank tears its side down
         comm.close()
     extra["pq_kmeans"] = {
         "workload": f"C3: Pq k-means 1M x 768 f32, 96 x 256 centroids, {iters3} iterations from SURVEY 8d's row picks, "
@@ -328,6 +349,7 @@ def run_ours(args) -> None:
                      "algorithmic_bytes_per_iter": it_bytes, "note": "two passes over x (assign, update) + codes"}}
     del x3
 
+    log("k-means done")
     # C5: one 12.5M x 128 shard per GPU (100M rows over 8 GPUs), M = 16; device-generated, no collective
     n5, M5, dsub5 = 12_500_000, 16, 8
     pq5 = rb.Pq(None, np.random.default_rng(5).normal(size=(M5, K_CENTROIDS, dsub5)).astype(np.float32))
@@ -351,6 +373,7 @@ def run_ours(args) -> None:
                                    "roofline": {"bound": "hbm", "achieved": c5_gbs, "peak": peaks["hbm_gbs"],
                                                 "unit": "GB/s per GPU", "frac": c5_gbs / peaks["hbm_gbs"]}}
     del x5, c5
+    log("C5 done")
     # C4: projected (Opq / GaussianOpq) encode + decode, 1M x 300, M = 30; exact-order FP32 rotation + encode / gather
     n4 = 1_000_000
     r4 = np.linalg.qr(np.random.default_rng(4).normal(size=(D, D)))[0].astype(np.float32)
@@ -380,6 +403,7 @@ def run_ours(args) -> None:
                                           "decode_frac": n4 * (4 * D + M) / (k0.elapsed_time(k1) * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     del rec4, c4
 
+    log("C4 done")
     if rank == 0:
         # roofline of the dominant kernel (the encode kernel is the whole step): algorithmic bytes per vector
         # = 4*d + M, against the measured HBM copy bandwidth — at the measured peaks the HBM bound

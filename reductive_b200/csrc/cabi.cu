@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -27,6 +28,21 @@ void set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(t_err, sizeof(t_err), fmt, ap);
     va_end(ap);
+}
+
+bool debug_sync_enabled()
+{
+    static const bool on = getenv("RB_DEBUG_SYNC") != nullptr;
+    return on;
+}
+
+void debug_sync_report(const char *file, int line)
+{
+    fprintf(stderr, "[rb sync] launched at %s:%d ...", file, line);
+    fflush(stderr);
+    const cudaError_t e = cudaDeviceSynchronize();
+    fprintf(stderr, " %s\n", e == cudaSuccess ? "done" : cudaGetErrorString(e));
+    fflush(stderr);
 }
 
 static std::mutex g_pool_mu;

@@ -37,10 +37,16 @@ cudaError_t pool_malloc(void **p, size_t bytes, cudaStream_t stream);
         if (_s != RB_OK) return _s;         \
     } while (0)
 
+// Debugging aid (RB_DEBUG_SYNC=1): synchronise after every launch and say where on stderr -- finds the kernel that
+// hangs or faults.
+bool debug_sync_enabled();
+void debug_sync_report(const char *file, int line);
+
 // Counts the launch and turns a launch-time error into RB_ERR_CUDA.
 #define RB_LAUNCH_CHECK()                                                                        \
     do {                                                                                         \
         ::rb::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        if (::rb::debug_sync_enabled()) ::rb::debug_sync_report(__FILE__, __LINE__);             \
         cudaError_t _e = cudaGetLastError();                                                     \
         if (_e != cudaSuccess) {                                                                 \
             ::rb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),          \

@@ -294,11 +294,15 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
     // rotated input: two more per-row values (margin = sMarg + sMargB * sqrt(max(sMargC + min score, 0)), see below)
     float *sMargB = sMarg + kMargRing * kTile, *sMargC = sMargB + kMargRing * kTile;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sMarg + (ROT ? 3 : 1) * kMargRing * kTile);
-    // acc_full is per epilogue SET (the set of unit u is u mod kSets), acc_empty per accumulator: a waiter then always
-    // waits for the phase that follows the last one it saw (a parity wait cannot tell "two phases later" from "not yet")
+    // acc_full has one barrier per (set, accumulator) pair = unit index mod 2 kSets: the units u and u + kSets of one set
+    // use DIFFERENT accumulators, so the MMA of u + kSets can complete before the set has even started to wait for u
+    // (its certificate of u - kSets may take long) -- on one barrier that is two completions, which a parity wait
+    // cannot tell from none: the set would sleep forever (this deadlocked ~1 launch in 50 of the rotated encode).
+    // Units u and u + 2 kSets share their accumulator and are therefore ordered.  acc_empty: one per accumulator.
     uint64_t *x_full = bars, *x_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 8, *acc_full = bars + 12,
-             *acc_empty = bars + 16, *b_full = bars + 18;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+             *acc_empty = bars + 12 + 2 * kSets, *b_full = bars + 14 + 2 * kSets;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 15 + 2 * kSets);
+    static_assert(16 + 2 * kSets <= 24, "barrier block of the shared-memory plan");
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
             mbar_init(&x_empty[i], 4);
             mbar_init(&acc_empty[i], 4);
         }
-        for (int i = 0; i < kSets; i++) mbar_init(&acc_full[i], 1);
+        for (int i = 0; i < 2 * kSets; i++) mbar_init(&acc_full[i], 1);
         for (int i = 0; i < 4; i++) {
             mbar_init(&a_full[i], 4);
             mbar_init(&a_empty[i], 1);
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
         for (long long t = t_first; t < p.n_tiles; t += t_stride, li++) {
             const int stage = (int)(li & 1);
             RB_PH(0);
-            mbar_wait(&x_full[stage], (li >> 1) & 1);
+            mbar_wait(&x_full[stage], (li >> 1) & 1, 1);
             RB_PH(1);
             const float4 *xr = reinterpret_cast<const float4 *>(sX + (size_t)stage * xs_bytes + (size_t)row * p.pitch_f * 4);
             float perr = 0.f;  // bound on the error of each component of this row (0: the row is exact)
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     if (bad || !(marg < 3.0e38f) || !(margb < 3.0e38f))
                         marg = __int_as_float(0x7fc00000);  // NaN: always re-decide exactly
                     RB_PH(2);
-                    mbar_wait(&a_empty[as], aph ^ 1);
+                    mbar_wait(&a_empty[as], aph ^ 1, 2);
                     RB_PH(3);
                     unsigned char *a = sA + (size_t)as * A_BYTES;
 #pragma unroll
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
             if (lane == 0) mbar_arrive(&x_empty[stage]);
             if (producer && t + 2 * t_stride < p.n_tiles) {
                 // refill this stage with the tile after next once all four converter warps have left it
-                mbar_wait(&x_empty[stage], (li >> 1) & 1);
+                mbar_wait(&x_empty[stage], (li >> 1) & 1, 3);
                 mbar_arrive_expect_tx(&x_full[stage], (uint32_t)xs_bytes);
                 tma_load_2d(sX + (size_t)stage * xs_bytes, &tmap, g * p.gm * DSUB, (int)((t + 2 * t_stride) * kTile), &x_full[stage]);
             }
@@ -492,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
             t += t_stride;
         }
         uint32_t n_flagged = 0;  // entries this warp has appended to its region (warp-uniform)
-        uint32_t full_ph = 0;    // phase of this set's acc_full barrier
+        uint32_t full_ix = (uint32_t)set, full_ph = 0;  // acc_full barrier (u mod 2 kSets) and phase ((u / 2 kSets) & 1) of unit u
         // MMA issue: the whole warp runs the code and one elected lane issues, so descriptors, phases and barrier
         // addresses stay warp-uniform.  The shared-memory descriptors differ only in the 14-bit start-address field of
         // their low word.  Unit v uses A stage v mod S, accumulator v mod 2, and completes on acc_full[v mod kSets].
@@ -502,17 +506,17 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
         const uint64_t b_desc0 = smem_desc_kmajor(smem_u32(sB), kCent * 16, 128);
         constexpr uint32_t A_STEP = A_BYTES >> 4, B_STEP = B_BYTES >> 4;                // per stage / per subquantizer
         constexpr uint32_t A_KS = (2 * kTile * 16) >> 4, B_KS = (2 * kCent * 16) >> 4;  // per K = 16 slice
-        // (unit, its A stage and phase, subquantizer, set) of the next unit this warp issues
+        // (unit, its A stage and phase, subquantizer, acc_full barrier) of the next unit this warp issues
         uint32_t iv = 0, i_as = 0, i_aph = 0, i_ml = 0, i_set = 0;
         auto issue_at = [&](uint32_t v) {  // position the issue state on unit v
             iv = v;
             i_as = v % (uint32_t)S;
             i_aph = (v / (uint32_t)S) & 1u;
             i_ml = v % (uint32_t)gm_cur;
-            i_set = v % (uint32_t)kSets;
+            i_set = v % (uint32_t)(2 * kSets);
         };
         auto issue_unit = [&]() {  // the accumulator iv mod 2 is free
-            mbar_wait(&a_full[i_as], i_aph);
+            mbar_wait(&a_full[i_as], i_aph, 4);
             tc_fence_after();
             const uint32_t a_lo = (uint32_t)a_desc0 + i_as * A_STEP, b_lo = (uint32_t)b_desc0 + i_ml * B_STEP;
 #pragma unroll
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
             tc_commit_warp(&a_empty[i_as]);
         };
         if (issuer) {
-            mbar_wait(b_full, 0);
+            mbar_wait(b_full, 0, 5);
             if (set >= 1) {  // units 0 and 1 start the pipeline (sets 1 and 2 issue them before their first scan)
                 issue_at((uint32_t)set - 1u);
                 if (iv < n_units) issue_unit();
@@ -531,14 +535,18 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
             issue_at((uint32_t)set + 2u);  // from now on: after scanning own unit u (= set, set + kSets, ...) issue u + 2
         }
         RB_PH_BEGIN();
-        for (uint32_t u = (uint32_t)set; t < p.n_tiles; u += kSets, full_ph ^= 1) {
+        for (uint32_t u = (uint32_t)set; t < p.n_tiles; u += kSets) {
             const long long grow = t * kTile + row;
             const int m = g * p.gm + ml;
             {
                 const uint32_t buf = u & 1;
                 const uint32_t taddr = taddr0 + buf * kCent;
                 RB_PH(0);
-                mbar_wait(&acc_full[set], full_ph);
+                // the previous unit may have ended in a divergent branch (flagged rows): the tcgen05.ld / elect.sync
+                // instructions below are warp-collective and need the warp converged
+                __syncwarp();
+                mbar_wait(&acc_full[full_ix], full_ph, 6);
+                __syncwarp();
                 RB_PH(1);
                 tc_fence_after();
                 // 256 F16 scores, two per register: register r of a 64-column load = columns (2r, 2r + 1).
@@ -573,10 +581,11 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 if (issuer && iv < n_units) {
                     // unit u + 2 goes into the accumulator this set has just read: wait for the set's other warps
-                    mbar_wait(&acc_empty[buf], (u >> 1) & 1);
+                    mbar_wait(&acc_empty[buf], (u >> 1) & 1, 7);
                     issue_unit();
-                    // advance by kSets units without divisions (i_set is unchanged)
+                    // advance by kSets units without divisions
                     iv += (uint32_t)kSets;
+                    i_set = i_set >= (uint32_t)kSets ? i_set - (uint32_t)kSets : i_set + (uint32_t)kSets;
                     i_as += (uint32_t)kSets;
                     while (i_as >= (uint32_t)S) {
                         i_as -= (uint32_t)S;
@@ -655,6 +664,12 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
             while (ml >= gm_cur && t < p.n_tiles) {
                 ml -= gm_cur;
                 t += t_stride;
+            }
+            if (full_ix >= (uint32_t)kSets) {  // u + kSets: the other barrier of this set; every second step a new phase
+                full_ix -= (uint32_t)kSets;
+                full_ph ^= 1;
+            } else {
+                full_ix += (uint32_t)kSets;
             }
         }
         if constexpr (!ROT)

@@ -3,6 +3,7 @@
 // Descriptor bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <stdint.h>
 
 namespace rb {
@@ -79,34 +80,41 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-// The whole retry loop lives in one asm block: a failed try sleeps in hardware (suspend-time hint) and a retry costs
-// the try itself and one branch -- a C-level loop around mbar_try_wait re-materialised the address and parity on every
-// iteration, and the spinning warps took a quarter of all issued instructions (ncu, encode_tc_kernel).
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// A failed try sleeps in hardware (suspend-time hint) before it is retried.  The retry loop must stay a C-level loop:
+// lanes of a warp can see the phase flip in different iterations, and only a loop the compiler knows about gets its
+// reconvergence point -- with the loop hidden inside one asm block the warp left it diverged now and then, and the
+// next warp-collective instruction (tcgen05.ld, elect.sync) hung the kernel (about 1 launch in 50 of the rotated encode).
+// -DRB_TC_WATCHDOG: a wait that lasts longer than ~1 s reports itself (block, thread, tag) and traps: deadlock hunting.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag = -1)
 {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "RB_MBAR_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra RB_MBAR_DONE_%=;\n\t"
-        "bra RB_MBAR_WAIT_%=;\n\t"
-        "RB_MBAR_DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(0x989680u)
-        : "memory");
+#ifdef RB_TC_WATCHDOG
+    const long long t0 = clock64();
+#endif
+    while (!mbar_try_wait(bar, parity)) {
+#ifdef RB_TC_WATCHDOG
+        if (clock64() - t0 > 2000000000ll) {
+            printf("[rb watchdog] block %d thread %d: wait tag %d parity %u on barrier %u timed out\n", (int)blockIdx.x,
+                   (int)threadIdx.x, tag, parity, smem_u32(bar));
+            __trap();
+        }
+#endif
+    }
+    (void)tag;
 }
 
 // Busy-polling wait (no suspend-time hint): lowest wake-up latency, for waits on the critical path of a pipeline.
 __device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "RB_MBAR_SPIN_%=:\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra RB_MBAR_SPUN_%=;\n\t"
-        "bra RB_MBAR_SPIN_%=;\n\t"
-        "RB_MBAR_SPUN_%=:\n\t}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
 }
 
 // ---- thread-block clusters --------------------------------------------------------------------------------
