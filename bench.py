@@ -30,8 +30,9 @@ METRIC = "quantize_batch_vectors_per_s"
 UNIT = "vectors/s"
 N_ROWS, M, K_CENTROIDS, DSUB = 2_000_000, 30, 256, 10
 D = M * DSUB
-# dram__bytes_read.sum + dram__bytes_write.sum of encode_tc_kernel<10> on this workload (ncu --set full, final round-1 build)
-ENCODE_DRAM_BYTES_PER_LAUNCH = 2.4573e9 + 0.0628e9
+# dram__bytes_read.sum + dram__bytes_write.sum of encode_tc_kernel<10, 0> on this workload (ncu --set full, round-2 build:
+# profiles/r2_encode_tc_final_ncu.txt)
+ENCODE_DRAM_BYTES_PER_LAUNCH = 2.4537e9 + 0.0708e9
 WORKLOAD = "C2: quantize_batch 2M x 300 f32 N(0,1), 30 subquantizers x 256 centroids, u8 codes"
 
 
@@ -415,7 +416,7 @@ def run_ours(args) -> None:
         tflops = N_ROWS * flops_per_vec / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"], "traffic": ENCODE_DRAM_BYTES_PER_LAUNCH,
-                    "traffic_source": "profiles/r1_encode_tc_final_ncu.txt (dram__bytes_read + write, one launch)",
+                    "traffic_source": "profiles/r2_encode_tc_final_ncu.txt (dram__bytes_read + write, one launch)",
                     "peak_source": peaks["source"],
                     "kernel_ms": kern_ms, "algorithmic_bytes_per_vector": bytes_per_vec,
                     "tensor_tflops_algorithmic": tflops, "tensor_frac_of_bf16_peak": tflops / peaks["bf16_tflops"],
