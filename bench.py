@@ -149,6 +149,10 @@ def run_ours(args) -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    # stdout carries exactly ONE line, the JSON: libraries that print banners there (NCCL's version line) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -224,6 +228,44 @@ def run_ours(args) -> None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_rows / float(te.item())
     e2e_ok = bool(torch.equal(ch.to(dev), codes[:e2e_rows]))
+    # the same call on a plain numpy array (pageable memory, what an ndarray caller hands over): the library stages
+    # it through pinned buffers of its own
+    xn = np.empty((e2e_rows, D), np.float32)
+    xn[:] = xh_np
+    cn = np.empty((e2e_rows, M), np.uint8)
+    pq.quantize_batch_into(xn, cn)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pq.quantize_batch_into(xn, cn)
+    pg_s = (time.perf_counter() - t0) / e2e_steps
+    tp = torch.tensor([pg_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    e2e_pageable = world * e2e_rows / float(tp.item())
+    e2e_pageable_ok = bool(np.array_equal(cn, ch_np))
+    # ... and from ONE process over all GPUs of the box (rb_pq_create_multi splits the rows; rank 0 only, others idle)
+    one_process = None
+    if torch.cuda.device_count() > 1:
+        barrier()
+        if rank == 0:
+            ndev = world if world > 1 else torch.cuda.device_count()
+            pqm = rb.Pq(None, q, devices=list(range(ndev)))
+            rows_m = 1_000_000 * ndev
+            xm = np.empty((rows_m, D), np.float32)
+            for i in range(0, rows_m, 1_000_000):
+                xm[i:i + 1_000_000] = xn[:1_000_000]
+            cm = np.empty((rows_m, M), np.uint8)
+            pqm.quantize_batch_into(xm, cm)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                pqm.quantize_batch_into(xm, cm)
+            dt = (time.perf_counter() - t0) / 2
+            one_process = {"devices": ndev, "rows": rows_m, "value": rows_m / dt, "unit": UNIT, "buffers": "pageable numpy",
+                           "codes_match": bool(np.array_equal(cm[:1_000_000], cn[:1_000_000]))}
+            del xm, cm, pqm
+        barrier()
+    del xn, cn
     if prev_affinity:
         os.sched_setaffinity(0, prev_affinity)
 
@@ -281,18 +323,8 @@ def run_ours(args) -> None:
     loss3 = torch.zeros((M3,), device=dev)
     log("k-means: initial centroids ready")
     if world > 1:
-        # NCCL may print its version banner on stdout when the library's communicator comes up: keep stdout for the
-        # one JSON line (file descriptor 1 points at stderr while the communicator is created)
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            comm = Comm()
-            km = ShardedKMeans(comm, x3, M3, K_CENTROIDS, dsub3)
-            torch.cuda.synchronize()
-        finally:
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+        comm = Comm()
+        km = ShardedKMeans(comm, x3, M3, K_CENTROIDS, dsub3)
         step3 = lambda c, l=None: km.iterate(c, l)  # noqa: E731
     else:
         packed3 = torch.empty((M3 * K_CENTROIDS * dsub3 + M3 * K_CENTROIDS + M3,), device=dev)
@@ -441,7 +473,7 @@ def run_ours(args) -> None:
                         "sample": f"{sample} rows of rank 0's batch, {cores} threads row-sharded "
                                   f"(single thread, as the reference runs it: {sample // cores / cpu_dt1:.0f} vectors/s)",
                         "codes_match_gpu": parity}
-        print(json.dumps({
+        line = json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -449,9 +481,13 @@ def run_ours(args) -> None:
                        "encode_algo": os.environ.get("RB_ENCODE_ALGO", "auto"), "parallelism": f"rows x{world}"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_rows * D * 4,
-                    "d2h_bytes_per_step": e2e_rows * M, "steps": e2e_steps, "codes_match_device_path": e2e_ok},
+                    "d2h_bytes_per_step": e2e_rows * M, "steps": e2e_steps, "codes_match_device_path": e2e_ok,
+                    "buffers": "pinned host memory (the contract's e2e); the fields below repeat the call on pageable memory",
+                    "pageable_value": e2e_pageable, "pageable_codes_match": e2e_pageable_ok,
+                    "one_process_all_devices": one_process},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra,
-        }))
+        })
+        os.write(json_fd, (line + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -8,13 +8,14 @@
  * Conventions
  *   - Strides are in ELEMENTS (like ndarray), may be any non-zero value for inputs; views with
  *     col_stride != 1 are packed on the device before the kernels run.
- *   - `mem_kind` says where the data pointers of that call live (RB_MEM_HOST: ordinary or pinned host
- *     memory, copied in chunks overlapped with the kernels; RB_MEM_DEVICE: device memory of the
+ *   - `mem_kind` says where the data pointers of that call live (RB_MEM_HOST: ordinary (pageable) or pinned host
+ *     memory, copied in chunks overlapped with the kernels -- pageable memory goes through pinned staging buffers
+ *     the library owns, so it reaches about the pinned transfer rate; RB_MEM_DEVICE: device memory of the
  *     CURRENT CUDA device, no copies).
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device-memory calls
  *     are asynchronous on that stream; host-memory calls return after the result is in host memory.
- *   - One process drives one GPU (the current device); a handle belongs to the device that was
- *     current when it was created.  Handles are immutable after creation: concurrent calls on one
+ *   - A handle belongs to the device that was current when it was created (rb_pq_create) or to the device list it
+ *     was given (rb_pq_create_multi: host-memory batches are split over the devices from this one process).  Handles are immutable after creation: concurrent calls on one
  *     handle from several threads / streams are legal (Pq is Sync in the reference, pq.rs:28).
  *   - There is NO CPU fallback: without a CUDA device every compute entry point returns
  *     RB_ERR_NO_DEVICE / RB_ERR_CUDA.
@@ -100,6 +101,16 @@ rb_status rb_set_kmeans_update(int ordered);
  * projection: HOST [d,d] row-major (d = M*dsub) or NULL.  RB_ERR_SHAPE when any extent is 0. */
 rb_status rb_pq_create(const float *quantizers, size_t n_subquantizers, size_t n_centroids,
                        size_t subquantizer_dim, const float *projection_or_null, rb_pq **out);
+/* The same quantizer replicated on several devices of this process.  The handle lives on devices[0];
+ * rb_pq_quantize_batch / rb_pq_reconstruct_batch with RB_MEM_HOST then split the rows into contiguous blocks over
+ * the devices (one host thread and one copy / compute pipeline per device, no collective: rows are independent).
+ * Device-memory calls use the replica of devices[0]. */
+rb_status rb_pq_create_multi(const float *quantizers, size_t n_subquantizers, size_t n_centroids,
+                             size_t subquantizer_dim, const float *projection_or_null, const int *devices,
+                             int n_devices, rb_pq **out);
+int rb_pq_n_devices(const rb_pq *pq);
+/* Host threads per pageable <-> pinned staging copy of the host-memory pipelines (default 4; process-wide). */
+rb_status rb_set_host_copy_threads(int n_threads);
 void rb_pq_destroy(rb_pq *pq);
 size_t rb_pq_quantized_len(const rb_pq *pq);         /* QuantizeVector::quantized_len     pq.rs:300 */
 size_t rb_pq_reconstructed_len(const rb_pq *pq);     /* Reconstruct::reconstructed_len    pq.rs:345 */

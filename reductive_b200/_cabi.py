@@ -38,7 +38,7 @@ PROJECT_AUTO, PROJECT_EXACT, PROJECT_TENSOR = 0, 1, 2
 EXPORTED_SYMBOLS = [
     "rb_last_error_message", "rb_abi_version", "rb_kernel_launch_count", "rb_set_encode_algo",
     "rb_set_kmeans_update", "rb_set_project_algo", "rb_release_scratch",
-    "rb_pq_create", "rb_pq_destroy", "rb_pq_quantized_len", "rb_pq_reconstructed_len",
+    "rb_pq_create", "rb_pq_create_multi", "rb_pq_n_devices", "rb_set_host_copy_threads", "rb_pq_destroy", "rb_pq_quantized_len", "rb_pq_reconstructed_len",
     "rb_pq_n_quantizer_centroids", "rb_pq_has_projection", "rb_pq_subquantizers", "rb_pq_projection",
     "rb_pq_quantize_batch", "rb_pq_quantize_vector", "rb_pq_reconstruct_batch", "rb_pq_reconstruct",
     "rb_check_quantizer_invariants", "rb_kmeans_packed_len", "rb_kmeans_assign_accumulate",
@@ -111,6 +111,9 @@ def _load() -> C.CDLL:
     lib.rb_set_kmeans_update.argtypes = [C.c_int]
     lib.rb_set_project_algo.argtypes = [C.c_int]
     lib.rb_pq_create.argtypes = [fp, sz, sz, sz, fp, C.POINTER(vp)]
+    lib.rb_pq_create_multi.argtypes = [fp, sz, sz, sz, fp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.rb_pq_n_devices.argtypes = [vp]
+    lib.rb_set_host_copy_threads.argtypes = [C.c_int]
     lib.rb_pq_destroy.argtypes = [vp]
     lib.rb_pq_destroy.restype = None
     for name in ("rb_pq_quantized_len", "rb_pq_reconstructed_len", "rb_pq_n_quantizer_centroids"):

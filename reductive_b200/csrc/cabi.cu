@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -140,6 +143,9 @@ struct rb_pq {
     ProjTensorOperands ptc_enc, ptc_dec;  // R / R^T limbs for the tcgen05 rotation (may be empty)
     float q_absmax = 0.f;        // max |centroid component| (bounds every gathered value); < 0: non-finite codebook
     std::vector<float> q_host, proj_host;
+    // rb_pq_create_multi: replicas of this quantizer on the other devices (owned by this handle); host-memory batch
+    // calls split their rows over this device and the replicas' devices
+    std::vector<rb_pq *> peers;
     DeviceCodebook cb() const { return DeviceCodebook{q_dev, cs_dev, M, k, dsub}; }
 };
 
@@ -311,32 +317,184 @@ void host_unpack(const void *src, size_t rows, size_t cols, void *dst, ptrdiff_t
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------
+// pageable host memory: library-owned pinned staging
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+// An ndarray caller hands ordinary (pageable) memory; a DMA from it is staged by the driver through a small pinned
+// buffer at a fraction of the PCIe rate and blocks the calling thread.  The host pipelines therefore copy pageable
+// chunks through pinned buffers of their own (several host threads per copy), which keeps the H2D / D2H copies
+// asynchronous and at the pinned rate.  Buffers are cached per host thread and device and live until the thread ends.
+bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+struct PinnedSet {
+    struct Buf {
+        void *p = nullptr;
+        size_t bytes = 0;
+    };
+    Buf bufs[4];  // in[0], in[1], out[0], out[1]
+    void *get(int i, size_t bytes)
+    {
+        Buf &b = bufs[i];
+        if (b.bytes < bytes) {
+            if (b.p) cudaFreeHost(b.p);
+            b.p = nullptr;
+            b.bytes = 0;
+            if (cudaHostAlloc(&b.p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+                (void)cudaGetLastError();
+                b.p = nullptr;
+                return nullptr;
+            }
+            b.bytes = bytes;
+        }
+        return b.p;
+    }
+};
+
+// Process-wide pool of staging sets (pinned allocations cost milliseconds: they are kept for the life of the
+// process and handed from call to call; concurrent calls each take their own set).
+struct PinnedLease {
+    PinnedSet *set = nullptr;
+    PinnedLease()
+    {
+        std::lock_guard<std::mutex> lock(mu());
+        if (!idle().empty()) {
+            set = idle().back();
+            idle().pop_back();
+        } else {
+            set = new PinnedSet();
+        }
+    }
+    ~PinnedLease()
+    {
+        std::lock_guard<std::mutex> lock(mu());
+        idle().push_back(set);
+    }
+    void *get(int i, size_t bytes) { return set->get(i, bytes); }
+    static std::mutex &mu()
+    {
+        static std::mutex m;
+        return m;
+    }
+    static std::vector<PinnedSet *> &idle()
+    {
+        static std::vector<PinnedSet *> v;
+        return v;
+    }
+};
+
+std::atomic<int> g_copy_threads{4};
+
+// dst[rows, row_bytes] (dense) <-> a host matrix with row pitch `pitch` bytes, split over a few host threads
+void par_copy_rows(char *dst, size_t dpitch, const char *src, size_t spitch, size_t row_bytes, size_t rows)
+{
+    const size_t total = rows * row_bytes;
+    int nt = g_copy_threads.load();
+    if (total < ((size_t)4 << 20) || nt <= 1) nt = 1;
+    auto work = [=](size_t r0, size_t r1) {
+        if (dpitch == row_bytes && spitch == row_bytes) {
+            memcpy(dst + r0 * row_bytes, src + r0 * row_bytes, (r1 - r0) * row_bytes);
+        } else {
+            for (size_t r = r0; r < r1; r++) memcpy(dst + r * dpitch, src + r * spitch, row_bytes);
+        }
+    };
+    if (nt == 1) {
+        work(0, rows);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (rows + (size_t)nt - 1) / (size_t)nt;
+    for (int t = 1; t < nt; t++) {
+        const size_t r0 = per * (size_t)t < rows ? per * (size_t)t : rows, r1 = r0 + per < rows ? r0 + per : rows;
+        if (r0 < r1) th.emplace_back(work, r0, r1);
+    }
+    work(0, per < rows ? per : rows);
+    for (auto &t : th) t.join();
+}
+
+// Run `body(replica, first row, rows)` for contiguous row blocks over the quantizer's devices, one host thread each.
+rb_status over_devices(const rb_pq *pq, size_t n, const std::function<rb_status(const rb_pq *, size_t, size_t)> &body)
+{
+    const size_t D = 1 + pq->peers.size();
+    if (D == 1 || n < 2 * D) {
+        RB_CUDA_TRY(cudaSetDevice(pq->device));
+        return body(pq, 0, n);
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    std::vector<rb_status> st(D, RB_OK);
+    std::vector<std::string> err(D);
+    std::vector<std::thread> th;
+    const size_t per = ((n + D - 1) / D + 127) / 128 * 128;  // whole 128-row tiles per device
+    for (size_t i = 0; i < D; i++) {
+        const size_t r0 = per * i < n ? per * i : n, r1 = r0 + per < n ? r0 + per : n;
+        if (r0 >= r1) continue;
+        const rb_pq *rep = i == 0 ? pq : pq->peers[i - 1];
+        th.emplace_back([&, i, rep, r0, r1]() {
+            if (cudaSetDevice(rep->device) != cudaSuccess) {
+                st[i] = RB_ERR_CUDA;
+                err[i] = "cudaSetDevice failed";
+                return;
+            }
+            st[i] = body(rep, r0, r1 - r0);
+            if (st[i] != RB_OK) err[i] = rb_last_error_message();
+        });
+    }
+    for (auto &t : th) t.join();
+    cudaSetDevice(prev);
+    for (size_t i = 0; i < D; i++)
+        if (st[i] != RB_OK) {
+            set_error("device %d: %s", i == 0 ? pq->device : pq->peers[i - 1]->device, err[i].c_str());
+            return st[i];
+        }
+    return RB_OK;
+}
+
+}  // namespace
+
 static rb_status quantize_batch_host(const rb_pq *pq, const float *x, size_t n, ptrdiff_t rs, ptrdiff_t cs,
                                      void *codes, int code_width, ptrdiff_t crs, ptrdiff_t ccs)
 {
-    const size_t d = pq->d, M = pq->M;
+    const size_t d = pq->d, M = pq->M, cw = (size_t)code_width;
     const bool in2d = (cs == 1 && rs >= (ptrdiff_t)d);
     const bool out2d = (ccs == 1 && crs >= (ptrdiff_t)M);
+    // DMA straight from / to the caller's memory only when it is pinned; otherwise through pinned staging buffers
+    const bool in_direct = in2d && host_is_pinned(x), out_direct = out2d && host_is_pinned(codes);
     const size_t chunk = host_chunk_rows(n, d * sizeof(float));
     HostPipe pipe;
     RB_TRY(pipe.init());
     Workspace xin[2], cout[2];
-    std::vector<float> xstage[2];
-    std::vector<unsigned char> cstage[2];
+    PinnedLease t_pinned;
+    float *sin[2] = {nullptr, nullptr};
+    unsigned char *sout[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) {
         RB_TRY(xin[i].alloc(chunk * d * sizeof(float), pipe.st[i]));
-        RB_TRY(cout[i].alloc(chunk * M * code_width, pipe.st[i]));
+        RB_TRY(cout[i].alloc(chunk * M * cw, pipe.st[i]));
+        if (!in_direct) sin[i] = reinterpret_cast<float *>(t_pinned.get(i, chunk * d * sizeof(float)));
+        if (!out_direct) sout[i] = reinterpret_cast<unsigned char *>(t_pinned.get(2 + i, chunk * M * cw));
+        if ((!in_direct && !sin[i]) || (!out_direct && !sout[i])) return fail(RB_ERR_CUDA, "cudaHostAlloc of a staging buffer failed");
     }
     // a strided host view keeps its meaning: without a projection the reference's row norms take the
     // sequential dot for non-unit column strides (see oracle.c); packing does not change that.
-    const int seq_norm = (!pq->proj_dev && cs != 1 && d > 1 && pq->dsub > 1) ? 1 : 0;
+    const bool seq_norm = !pq->proj_dev && cs != 1 && d > 1 && pq->dsub > 1;
     size_t pending_r0[2] = {0, 0}, pending_rows[2] = {0, 0};
-    auto drain = [&](int slot) -> rb_status {
-        if (pending_rows[slot] && !out2d) {
-            RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[slot]));
-            host_unpack(cstage[slot].data(), pending_rows[slot], M,
-                        reinterpret_cast<char *>(codes) + (ptrdiff_t)pending_r0[slot] * crs * code_width, crs, ccs,
-                        (size_t)code_width);
+    auto drain = [&](int slot) -> rb_status {  // the slot's previous chunk is complete; deliver staged codes
+        RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[slot]));
+        if (pending_rows[slot]) {
+            char *dst = reinterpret_cast<char *>(codes) + (ptrdiff_t)pending_r0[slot] * crs * (ptrdiff_t)cw;
+            if (out2d)
+                par_copy_rows(dst, (size_t)crs * cw, reinterpret_cast<const char *>(sout[slot]), M * cw, M * cw, pending_rows[slot]);
+            else
+                host_unpack(sout[slot], pending_rows[slot], M, dst, crs, ccs, cw);
         }
         pending_rows[slot] = 0;
         return RB_OK;
@@ -347,73 +505,73 @@ static rb_status quantize_batch_host(const rb_pq *pq, const float *x, size_t n, 
         cudaStream_t st = pipe.st[slot];
         RB_TRY(drain(slot));
         float *xd = xin[slot].as<float>();
-        if (in2d && rs == (ptrdiff_t)d) {  // contiguous: one linear DMA (2-D copies of 1.2 KB rows run at ~1/5 speed)
-            RB_CUDA_TRY(cudaMemcpyAsync(xd, x + (ptrdiff_t)r0 * rs, rows * d * sizeof(float), cudaMemcpyHostToDevice, st));
-        } else if (in2d) {
-            RB_CUDA_TRY(cudaMemcpy2DAsync(xd, d * sizeof(float), x + (ptrdiff_t)r0 * rs, (size_t)rs * sizeof(float),
-                                          d * sizeof(float), rows, cudaMemcpyHostToDevice, st));
+        const float *xsrc = x + (ptrdiff_t)r0 * rs;
+        if (in_direct && rs == (ptrdiff_t)d) {  // contiguous: one linear DMA (2-D copies of 1.2 KB rows run at ~1/5 speed)
+            RB_CUDA_TRY(cudaMemcpyAsync(xd, xsrc, rows * d * sizeof(float), cudaMemcpyHostToDevice, st));
+        } else if (in_direct) {
+            RB_CUDA_TRY(cudaMemcpy2DAsync(xd, d * sizeof(float), xsrc, (size_t)rs * sizeof(float), d * sizeof(float), rows,
+                                          cudaMemcpyHostToDevice, st));
         } else {
-            RB_CUDA_TRY(cudaStreamSynchronize(st));  // staging buffer of this slot is free again
-            xstage[slot].resize(rows * d);
-            host_pack(x + (ptrdiff_t)r0 * rs, rows, d, rs, cs, sizeof(float), xstage[slot].data());
-            RB_CUDA_TRY(cudaMemcpyAsync(xd, xstage[slot].data(), rows * d * sizeof(float), cudaMemcpyHostToDevice, st));
+            if (in2d)
+                par_copy_rows(reinterpret_cast<char *>(sin[slot]), d * sizeof(float), reinterpret_cast<const char *>(xsrc),
+                              (size_t)rs * sizeof(float), d * sizeof(float), rows);
+            else
+                host_pack(xsrc, rows, d, rs, cs, sizeof(float), sin[slot]);
+            RB_CUDA_TRY(cudaMemcpyAsync(xd, sin[slot], rows * d * sizeof(float), cudaMemcpyHostToDevice, st));
         }
-        const float *src = xd;
-        Workspace rx;
-        if (pq->proj_dev) {
-            RB_TRY(rx.alloc(rows * d * sizeof(float), st));
-            RB_TRY(launch_project(xd, rows, d, (ptrdiff_t)d, 1, pq->proj_dev, 0, rx.as<float>(), st));
-            src = rx.as<float>();
-        }
-        RB_TRY(encode_device(pq->cb(), &pq->tc, src, rows, (ptrdiff_t)d, seq_norm, cout[slot].p, code_width,
-                             (ptrdiff_t)M, 1, st));
-        if (out2d && crs == (ptrdiff_t)M) {
-            RB_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char *>(codes) + (ptrdiff_t)r0 * crs * code_width, cout[slot].p,
-                                        rows * M * code_width, cudaMemcpyDeviceToHost, st));
-        } else if (out2d) {
-            RB_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<char *>(codes) + (ptrdiff_t)r0 * crs * code_width,
-                                          (size_t)crs * code_width, cout[slot].p, M * code_width, M * code_width, rows,
-                                          cudaMemcpyDeviceToHost, st));
+        if (seq_norm)
+            RB_TRY(encode_device(pq->cb(), &pq->tc, xd, rows, (ptrdiff_t)d, 1, cout[slot].p, code_width, (ptrdiff_t)M, 1, st));
+        else  // the same path as device-resident batches (tensor rotation + tensor encode where the shape allows)
+            RB_TRY(quantize_batch_device(pq, xd, rows, (ptrdiff_t)d, 1, cout[slot].p, code_width, (ptrdiff_t)M, 1, st));
+        char *cdst = reinterpret_cast<char *>(codes) + (ptrdiff_t)r0 * crs * (ptrdiff_t)cw;
+        if (out_direct && crs == (ptrdiff_t)M) {
+            RB_CUDA_TRY(cudaMemcpyAsync(cdst, cout[slot].p, rows * M * cw, cudaMemcpyDeviceToHost, st));
+        } else if (out_direct) {
+            RB_CUDA_TRY(cudaMemcpy2DAsync(cdst, (size_t)crs * cw, cout[slot].p, M * cw, M * cw, rows, cudaMemcpyDeviceToHost, st));
         } else {
-            cstage[slot].resize(rows * M * code_width);
-            RB_CUDA_TRY(cudaMemcpyAsync(cstage[slot].data(), cout[slot].p, rows * M * code_width,
-                                        cudaMemcpyDeviceToHost, st));
+            RB_CUDA_TRY(cudaMemcpyAsync(sout[slot], cout[slot].p, rows * M * cw, cudaMemcpyDeviceToHost, st));
             pending_r0[slot] = r0;
             pending_rows[slot] = rows;
         }
     }
-    for (int i = 0; i < 2; i++) {
-        RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[i]));
-        RB_TRY(drain(i));
-    }
+    for (int i = 0; i < 2; i++) RB_TRY(drain(i));
     return RB_OK;
 }
 
 static rb_status reconstruct_batch_host(const rb_pq *pq, const void *codes, int code_width, size_t n, ptrdiff_t crs,
                                         ptrdiff_t ccs, float *out, ptrdiff_t ors, ptrdiff_t ocs)
 {
-    const size_t d = pq->d, M = pq->M;
+    const size_t d = pq->d, M = pq->M, cw = (size_t)code_width;
     const bool in2d = (ccs == 1 && crs >= (ptrdiff_t)M);
     const bool out2d = (ocs == 1 && ors >= (ptrdiff_t)d);
+    const bool in_direct = in2d && host_is_pinned(codes), out_direct = out2d && host_is_pinned(out);
     const size_t chunk = host_chunk_rows(n, d * sizeof(float));
     HostPipe pipe;
     RB_TRY(pipe.init());
     Workspace cin[2], yout[2], flag;
-    std::vector<unsigned char> cstage[2];
-    std::vector<float> ystage[2];
+    PinnedLease t_pinned;
+    unsigned char *sin[2] = {nullptr, nullptr};
+    float *sout[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; i++) {
-        RB_TRY(cin[i].alloc(chunk * M * code_width, pipe.st[i]));
+        RB_TRY(cin[i].alloc(chunk * M * cw, pipe.st[i]));
         RB_TRY(yout[i].alloc(chunk * d * sizeof(float), pipe.st[i]));
+        if (!in_direct) sin[i] = reinterpret_cast<unsigned char *>(t_pinned.get(i, chunk * M * cw));
+        if (!out_direct) sout[i] = reinterpret_cast<float *>(t_pinned.get(2 + i, chunk * d * sizeof(float)));
+        if ((!in_direct && !sin[i]) || (!out_direct && !sout[i])) return fail(RB_ERR_CUDA, "cudaHostAlloc of a staging buffer failed");
     }
     RB_TRY(flag.alloc(sizeof(int), pipe.st[0]));
     RB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int), pipe.st[0]));
     RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[0]));
     size_t pending_r0[2] = {0, 0}, pending_rows[2] = {0, 0};
     auto drain = [&](int slot) -> rb_status {
-        if (pending_rows[slot] && !out2d) {
-            RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[slot]));
-            host_unpack(ystage[slot].data(), pending_rows[slot], d, out + (ptrdiff_t)pending_r0[slot] * ors, ors, ocs,
-                        sizeof(float));
+        RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[slot]));
+        if (pending_rows[slot]) {
+            float *dst = out + (ptrdiff_t)pending_r0[slot] * ors;
+            if (out2d)
+                par_copy_rows(reinterpret_cast<char *>(dst), (size_t)ors * sizeof(float), reinterpret_cast<const char *>(sout[slot]),
+                              d * sizeof(float), d * sizeof(float), pending_rows[slot]);
+            else
+                host_unpack(sout[slot], pending_rows[slot], d, dst, ors, ocs, sizeof(float));
         }
         pending_rows[slot] = 0;
         return RB_OK;
@@ -423,39 +581,33 @@ static rb_status reconstruct_batch_host(const rb_pq *pq, const void *codes, int 
         const size_t rows = n - r0 < chunk ? n - r0 : chunk;
         cudaStream_t st = pipe.st[slot];
         RB_TRY(drain(slot));
-        const char *csrc = reinterpret_cast<const char *>(codes) + (ptrdiff_t)r0 * crs * code_width;
-        if (in2d && crs == (ptrdiff_t)M) {
-            RB_CUDA_TRY(cudaMemcpyAsync(cin[slot].p, csrc, rows * M * code_width, cudaMemcpyHostToDevice, st));
-        } else if (in2d) {
-            RB_CUDA_TRY(cudaMemcpy2DAsync(cin[slot].p, M * code_width, csrc, (size_t)crs * code_width, M * code_width,
-                                          rows, cudaMemcpyHostToDevice, st));
+        const char *csrc = reinterpret_cast<const char *>(codes) + (ptrdiff_t)r0 * crs * (ptrdiff_t)cw;
+        if (in_direct && crs == (ptrdiff_t)M) {
+            RB_CUDA_TRY(cudaMemcpyAsync(cin[slot].p, csrc, rows * M * cw, cudaMemcpyHostToDevice, st));
+        } else if (in_direct) {
+            RB_CUDA_TRY(cudaMemcpy2DAsync(cin[slot].p, M * cw, csrc, (size_t)crs * cw, M * cw, rows, cudaMemcpyHostToDevice, st));
         } else {
-            RB_CUDA_TRY(cudaStreamSynchronize(st));
-            cstage[slot].resize(rows * M * code_width);
-            host_pack(csrc, rows, M, crs, ccs, (size_t)code_width, cstage[slot].data());
-            RB_CUDA_TRY(cudaMemcpyAsync(cin[slot].p, cstage[slot].data(), rows * M * code_width,
-                                        cudaMemcpyHostToDevice, st));
+            if (in2d)
+                par_copy_rows(reinterpret_cast<char *>(sin[slot]), M * cw, csrc, (size_t)crs * cw, M * cw, rows);
+            else
+                host_pack(csrc, rows, M, crs, ccs, cw, sin[slot]);
+            RB_CUDA_TRY(cudaMemcpyAsync(cin[slot].p, sin[slot], rows * M * cw, cudaMemcpyHostToDevice, st));
         }
         RB_TRY(reconstruct_batch_device(pq, cin[slot].p, code_width, rows, (ptrdiff_t)M, 1, yout[slot].as<float>(),
                                         (ptrdiff_t)d, 1, flag.as<int>(), st));
-        if (out2d && ors == (ptrdiff_t)d) {
-            RB_CUDA_TRY(cudaMemcpyAsync(out + (ptrdiff_t)r0 * ors, yout[slot].p, rows * d * sizeof(float),
-                                        cudaMemcpyDeviceToHost, st));
-        } else if (out2d) {
-            RB_CUDA_TRY(cudaMemcpy2DAsync(out + (ptrdiff_t)r0 * ors, (size_t)ors * sizeof(float), yout[slot].p,
-                                          d * sizeof(float), d * sizeof(float), rows, cudaMemcpyDeviceToHost, st));
+        float *odst = out + (ptrdiff_t)r0 * ors;
+        if (out_direct && ors == (ptrdiff_t)d) {
+            RB_CUDA_TRY(cudaMemcpyAsync(odst, yout[slot].p, rows * d * sizeof(float), cudaMemcpyDeviceToHost, st));
+        } else if (out_direct) {
+            RB_CUDA_TRY(cudaMemcpy2DAsync(odst, (size_t)ors * sizeof(float), yout[slot].p, d * sizeof(float), d * sizeof(float),
+                                          rows, cudaMemcpyDeviceToHost, st));
         } else {
-            ystage[slot].resize(rows * d);
-            RB_CUDA_TRY(cudaMemcpyAsync(ystage[slot].data(), yout[slot].p, rows * d * sizeof(float),
-                                        cudaMemcpyDeviceToHost, st));
+            RB_CUDA_TRY(cudaMemcpyAsync(sout[slot], yout[slot].p, rows * d * sizeof(float), cudaMemcpyDeviceToHost, st));
             pending_r0[slot] = r0;
             pending_rows[slot] = rows;
         }
     }
-    for (int i = 0; i < 2; i++) {
-        RB_CUDA_TRY(cudaStreamSynchronize(pipe.st[i]));
-        RB_TRY(drain(i));
-    }
+    for (int i = 0; i < 2; i++) RB_TRY(drain(i));
     int bad = 0;
     RB_CUDA_TRY(cudaMemcpy(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (bad) return fail(RB_ERR_CODE_RANGE, "a code is >= the number of centroids (%zu)", pq->k);
@@ -557,9 +709,68 @@ rb_status rb_pq_create(const float *quantizers, size_t M, size_t k, size_t dsub,
     return RB_OK;
 }
 
+rb_status rb_pq_create_multi(const float *quantizers, size_t M, size_t k, size_t dsub, const float *projection,
+                             const int *devices, int n_devices, rb_pq **out)
+{
+    if (!out) return fail(RB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!devices || n_devices <= 0) return fail(RB_ERR_INVALID, "no devices");
+    RB_TRY(require_device());
+    int count = 0, prev = 0;
+    RB_CUDA_TRY(cudaGetDeviceCount(&count));
+    for (int i = 0; i < n_devices; i++)
+        if (devices[i] < 0 || devices[i] >= count) return fail(RB_ERR_INVALID, "device %d is not visible (%d devices)", devices[i], count);
+    cudaGetDevice(&prev);
+    std::vector<rb_pq *> reps;
+    rb_status st = RB_OK;
+    for (int i = 0; i < n_devices && st == RB_OK; i++) {
+        rb_pq *r = nullptr;
+        if (cudaSetDevice(devices[i]) != cudaSuccess) st = fail(RB_ERR_CUDA, "cudaSetDevice(%d) failed", devices[i]);
+        if (st == RB_OK) st = rb_pq_create(quantizers, M, k, dsub, projection, &r);
+        if (r) reps.push_back(r);
+    }
+    cudaSetDevice(prev);
+    if (st != RB_OK) {
+        for (rb_pq *r : reps) rb_pq_destroy(r);
+        return st;
+    }
+    reps[0]->peers.assign(reps.begin() + 1, reps.end());
+    *out = reps[0];
+    return RB_OK;
+}
+
+int rb_pq_n_devices(const rb_pq *pq) { return pq ? 1 + (int)pq->peers.size() : 0; }
+
+rb_status rb_set_host_copy_threads(int n_threads)
+{
+    if (n_threads < 1 || n_threads > 64) return fail(RB_ERR_INVALID, "n_threads must be in [1, 64]");
+    g_copy_threads.store(n_threads);
+    return RB_OK;
+}
+
 void rb_pq_destroy(rb_pq *pq)
 {
     if (!pq) return;
+    if (!pq->peers.empty()) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        for (rb_pq *r : pq->peers) rb_pq_destroy(r);
+        pq->peers.clear();
+        cudaSetDevice(pq->device);
+        pq->tc.release();
+        pq->ptc_enc.release();
+        pq->ptc_dec.release();
+        cudaFree(pq->q_dev);
+        cudaFree(pq->cs_dev);
+        cudaFree(pq->proj_dev);
+        cudaFree(pq->projt_dev);
+        cudaSetDevice(prev);
+        delete pq;
+        return;
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != pq->device) cudaSetDevice(pq->device);
     pq->tc.release();
     pq->ptc_enc.release();
     pq->ptc_dec.release();
@@ -567,6 +778,7 @@ void rb_pq_destroy(rb_pq *pq)
     cudaFree(pq->cs_dev);
     cudaFree(pq->proj_dev);
     cudaFree(pq->projt_dev);
+    if (cur != pq->device) cudaSetDevice(cur);
     delete pq;
 }
 
@@ -601,7 +813,11 @@ rb_status rb_pq_quantize_batch(const rb_pq *pq, const float *x, size_t n, ptrdif
     RB_TRY(require_device());
     if (mem_kind == RB_MEM_DEVICE)
         return quantize_batch_device(pq, x, n, rs, cs, codes, code_width, crs, ccs, (cudaStream_t)stream);
-    return quantize_batch_host(pq, x, n, rs, cs, codes, code_width, crs, ccs);
+    // host memory: contiguous row blocks over the quantizer's devices (one device unless rb_pq_create_multi made it)
+    return over_devices(pq, n, [&](const rb_pq *rep, size_t r0, size_t rows) {
+        return quantize_batch_host(rep, x + (ptrdiff_t)r0 * rs, rows, rs, cs,
+                                   reinterpret_cast<char *>(codes) + (ptrdiff_t)r0 * crs * code_width, code_width, crs, ccs);
+    });
 }
 
 rb_status rb_pq_quantize_vector(const rb_pq *pq, const float *x, ptrdiff_t sx, void *codes, int code_width,
@@ -656,7 +872,11 @@ rb_status rb_pq_reconstruct_batch(const rb_pq *pq, const void *codes, int code_w
     if (n == 0) return RB_OK;
     if (!codes || !out) return fail(RB_ERR_INVALID, "NULL data pointer");
     RB_TRY(require_device());
-    if (mem_kind == RB_MEM_HOST) return reconstruct_batch_host(pq, codes, code_width, n, crs, ccs, out, ors, ocs);
+    if (mem_kind == RB_MEM_HOST)
+        return over_devices(pq, n, [&](const rb_pq *rep, size_t r0, size_t rows) {
+            return reconstruct_batch_host(rep, reinterpret_cast<const char *>(codes) + (ptrdiff_t)r0 * crs * code_width, code_width,
+                                          rows, crs, ccs, out + (ptrdiff_t)r0 * ors, ors, ocs);
+        });
     cudaStream_t st = (cudaStream_t)stream;
     Workspace flag;
     RB_TRY(flag.alloc(sizeof(int), st));

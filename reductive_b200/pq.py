@@ -176,8 +176,10 @@ class Pq(QuantizeVector, Reconstruct, TrainPq):
 
     Mirror of reductive::pq::Pq<f32> (src/pq/pq.rs:29-32)."""
 
-    def __init__(self, projection: Optional[np.ndarray], quantizers: np.ndarray):
-        # Pq::new, pq.rs:38-61
+    def __init__(self, projection: Optional[np.ndarray], quantizers: np.ndarray,
+                 devices: Optional[Sequence[int]] = None):
+        # Pq::new, pq.rs:38-61.  `devices`: replicate the quantizer on several GPUs of this process
+        # (rb_pq_create_multi); host-memory batches are then split over them.
         q = np.ascontiguousarray(quantizers, np.float32)
         if q.ndim != 3 or q.size == 0:
             raise ReductivePanic("Attempted to construct a product quantizer without quantizers.")
@@ -189,7 +191,12 @@ class Pq(QuantizeVector, Reconstruct, TrainPq):
                 raise ReductivePanic(
                     f"Incorrect projection matrix shape, was: {list(p.shape)}, should be [{M * dsub}, {M * dsub}]")
         self._h = C.c_void_p()
-        check(lib.rb_pq_create(q.ctypes.data, M, k, dsub, None if p is None else p.ctypes.data, C.byref(self._h)))
+        if devices is not None and len(devices) > 0:
+            dev = (C.c_int * len(devices))(*[int(v) for v in devices])
+            check(lib.rb_pq_create_multi(q.ctypes.data, M, k, dsub, None if p is None else p.ctypes.data, dev,
+                                         len(devices), C.byref(self._h)))
+        else:
+            check(lib.rb_pq_create(q.ctypes.data, M, k, dsub, None if p is None else p.ctypes.data, C.byref(self._h)))
 
     @classmethod
     def _from_handle(cls, handle: C.c_void_p) -> "Pq":

@@ -45,3 +45,31 @@ def test_multi_gpu_training_more_devices_than_subquantizers():
     one = rb.Pq.train_pq_using(M, bits, 3, 1, x, None, initial_centroids=init)
     many = rb.Pq.train_pq_using(M, bits, 3, 1, x, None, initial_centroids=init, devices=devs[:4])
     assert np.array_equal(one.subquantizers().view(np.int32), many.subquantizers().view(np.int32))
+
+
+@pytest.mark.parametrize("projected", [False, True])
+def test_host_batches_split_over_devices_from_one_process(oracle, projected):
+    """rb_pq_create_multi: quantize_batch / reconstruct_batch on plain (pageable) numpy arrays, rows split over every
+    GPU of the box through the C ABI -- the same bits as the oracle (and hence as one GPU)."""
+    import reductive_b200 as rb
+    from tests.util import orthonormal, random_codebook
+
+    devs = _devices()
+    if len(devs) < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n, M, k, dsub = 300_001, 10, 256, 10
+    q = random_codebook(M, k, dsub, 3)
+    r = orthonormal(M * dsub, 4) if projected else None
+    x = normal((n, M * dsub), 5)
+    pq = rb.Pq(r, q, devices=devs)
+    codes = pq.quantize_batch(x, np.uint8)
+    one = rb.Pq(r, q)
+    assert np.array_equal(codes, one.quantize_batch(x, np.uint8))
+    sample = np.random.default_rng(6).choice(n, 4000, replace=False)
+    assert np.array_equal(codes[sample], oracle.quantize_batch(q, r, x[sample], np.uint8))
+    rec = pq.reconstruct_batch(codes)
+    want = one.reconstruct_batch(codes)
+    if projected:
+        assert np.abs(rec - want).max() <= 1e-5 * np.abs(want).max()
+    else:
+        assert np.array_equal(rec, want)

@@ -588,3 +588,23 @@ def test_tensor_margin_holds_across_scales_and_widths(oracle, dsub, scale):
     codes = rb.Pq(None, q).quantize_batch(x, np.uint8)
     want = oracle.quantize_batch(q, None, x, np.uint8, n_threads=8)
     assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ"
+
+
+def test_pageable_and_pinned_host_buffers_give_the_same_codes(oracle, torch_cuda):
+    """The host-memory pipeline stages pageable memory through pinned buffers of its own (several chunks, both
+    slots, strided rows); pinned memory is copied from directly."""
+    torch = torch_cuda
+    n, M, k, dsub = 200_000, 10, 256, 10  # 240 MB: four 64 MB chunks
+    q = random_codebook(M, k, dsub, 11)
+    pq = rb.Pq(None, q)
+    x = normal((n, M * dsub + 4), 12)[:, : M * dsub]  # row pitch > d: strided rows
+    codes = pq.quantize_batch(x, np.uint8)
+    xp = torch.empty((n, M * dsub), dtype=torch.float32, pin_memory=True)
+    xp.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+    cp = torch.empty((n, M), dtype=torch.uint8, pin_memory=True)
+    pq.quantize_batch_into(xp.numpy(), cp.numpy())
+    assert np.array_equal(codes, cp.numpy())
+    sample = np.random.default_rng(13).choice(n, 3000, replace=False)
+    assert np.array_equal(codes[sample], oracle.quantize_batch(q, None, np.ascontiguousarray(x[sample]), np.uint8))
+    rec = pq.reconstruct_batch(codes)
+    assert np.array_equal(rec[sample], oracle.reconstruct_batch(q, None, codes[sample]))
