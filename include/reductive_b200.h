@@ -218,6 +218,26 @@ rb_status rb_project_rows(const float *x, size_t n, size_t d, ptrdiff_t x_row_st
                           ptrdiff_t x_col_stride, const float *r_dev, int transpose_r, float *out,
                           void *stream);
 
+/* ---- A = f64 --------------------------------------------------------------------------------------- */
+
+/* Pq<A> is generic over NdFloat (pq.rs:29-32,196-203; linalg.rs:150-156); every configuration this library was built
+ * for and every known caller (finalfusion's quantized embeddings) uses A = f32, and the kernels here are f32 only.
+ * A binding routes its f64 instantiation to these entry points, which all return RB_ERR_UNSUPPORTED with a message
+ * (no silent down-conversion: f32 arithmetic cannot reproduce the reference's f64 codes bit for bit).  The binding
+ * keeps calling the reference's own CPU code for f64. */
+rb_status rb_pq_create_f64(const double *quantizers, size_t n_subquantizers, size_t n_centroids,
+                           size_t subquantizer_dim, const double *projection_or_null, rb_pq **out);
+rb_status rb_pq_quantize_batch_f64(const rb_pq *pq, const double *x, size_t n, ptrdiff_t x_row_stride,
+                                   ptrdiff_t x_col_stride, void *codes, int code_width, ptrdiff_t code_row_stride,
+                                   ptrdiff_t code_col_stride, int mem_kind, void *stream);
+rb_status rb_pq_reconstruct_batch_f64(const rb_pq *pq, const void *codes, int code_width, size_t n,
+                                      ptrdiff_t code_row_stride, ptrdiff_t code_col_stride, double *out,
+                                      ptrdiff_t out_row_stride, ptrdiff_t out_col_stride, int mem_kind, void *stream);
+rb_status rb_pq_train_f64(const double *instances, size_t n, size_t d, ptrdiff_t row_stride, ptrdiff_t col_stride,
+                          size_t n_subquantizers, uint32_t n_subquantizer_bits, size_t n_iterations,
+                          size_t n_attempts, const double *initial_centroids, double *loss_out, int mem_kind,
+                          void *stream, rb_pq **out);
+
 /* ---- multi-GPU training (data-parallel Pq k-means; NCCL is called inside the library) ------------- */
 
 /* The reference trains the M subquantizers as M independent Rayon tasks (pq.rs:226-241), each a sequential k-means

@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = [
     "rb_kmeans_finalize", "rb_pq_train", "rb_project_rows",
     "rb_dist_subquantizer_range", "rb_comm_unique_id", "rb_comm_create", "rb_comm_destroy", "rb_comm_rank",
     "rb_comm_world", "rb_kmeans_dist_create", "rb_kmeans_dist_iterate", "rb_kmeans_dist_destroy", "rb_pq_train_dist",
-    "rb_pq_train_multi",
+    "rb_pq_train_multi", "rb_pq_create_f64", "rb_pq_quantize_batch_f64", "rb_pq_reconstruct_batch_f64", "rb_pq_train_f64",
 ]
 
 

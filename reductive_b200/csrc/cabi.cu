@@ -1066,7 +1066,11 @@ rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t rs, 
         ldx = (ptrdiff_t)d;
     }
 
-    Workspace cen, packed, loss_dev;
+    Workspace cen, packed, loss_dev, sumsq;
+    // sum ||x||^2 per subquantizer once (the instances never change): FP64, fixed order, so that the losses that rank
+    // the attempts (pq.rs:183-187) are run-to-run identical and free of float-atomic cancellation noise
+    RB_TRY(sumsq.alloc(M * sizeof(double), st));
+    RB_TRY(launch_sumsq64(x, n, ldx, M, dsub, sumsq.as<double>(), st));
     RB_TRY(cen.alloc(qn * sizeof(float), st));
     RB_TRY(packed.alloc(rb_kmeans_packed_len(M, k, dsub) * sizeof(float), st));
     RB_TRY(loss_dev.alloc(M * sizeof(float), st));
@@ -1076,7 +1080,7 @@ rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t rs, 
         for (size_t it = 0; it < n_iterations; it++) {  // kmeans.rs:279-284
             RB_TRY(rb_kmeans_assign_accumulate(x, n, ldx, cen.as<float>(), M, k, dsub, packed.as<float>(), st));
             RB_TRY(launch_kmeans_finalize(packed.as<float>(), M, k, dsub, n, cen.as<float>(),
-                                          it + 1 == n_iterations ? loss_dev.as<float>() : nullptr, st));
+                                          it + 1 == n_iterations ? loss_dev.as<float>() : nullptr, st, sumsq.as<double>()));
         }
         RB_CUDA_TRY(cudaMemcpyAsync(cand_q.data(), cen.p, qn * sizeof(float), cudaMemcpyDeviceToHost, st));
         RB_CUDA_TRY(cudaMemcpyAsync(cand_loss.data(), loss_dev.p, M * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1092,6 +1096,39 @@ rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t rs, 
     }
     if (loss_out) memcpy(loss_out, best_loss.data(), M * sizeof(float));
     return rb_pq_create(best_q.data(), M, k, dsub, nullptr, out);
+}
+
+// ---- A = f64: defined answers, no silent down-conversion (include/reductive_b200.h) -------------------------------
+static rb_status f64_unsupported(const char *what)
+{
+    return fail(RB_ERR_UNSUPPORTED,
+                "%s: this library's kernels are f32 only (Pq<f64> stays on the reference's CPU path; f32 arithmetic cannot "
+                "reproduce f64 codes bit for bit)", what);
+}
+
+rb_status rb_pq_create_f64(const double *, size_t, size_t, size_t, const double *, rb_pq **out)
+{
+    if (out) *out = nullptr;
+    return f64_unsupported("rb_pq_create_f64");
+}
+
+rb_status rb_pq_quantize_batch_f64(const rb_pq *, const double *, size_t, ptrdiff_t, ptrdiff_t, void *, int, ptrdiff_t, ptrdiff_t,
+                                   int, void *)
+{
+    return f64_unsupported("rb_pq_quantize_batch_f64");
+}
+
+rb_status rb_pq_reconstruct_batch_f64(const rb_pq *, const void *, int, size_t, ptrdiff_t, ptrdiff_t, double *, ptrdiff_t,
+                                      ptrdiff_t, int, void *)
+{
+    return f64_unsupported("rb_pq_reconstruct_batch_f64");
+}
+
+rb_status rb_pq_train_f64(const double *, size_t, size_t, ptrdiff_t, ptrdiff_t, size_t, uint32_t, size_t, size_t, const double *,
+                          double *, int, void *, rb_pq **out)
+{
+    if (out) *out = nullptr;
+    return f64_unsupported("rb_pq_train_f64");
 }
 
 rb_status rb_project_rows(const float *x, size_t n, size_t d, ptrdiff_t rs, ptrdiff_t cs, const float *r_dev,

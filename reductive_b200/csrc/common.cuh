@@ -229,8 +229,12 @@ rb_status launch_project(const float *x, size_t n, size_t d, ptrdiff_t rsx, ptrd
 rb_status launch_kmeans_accumulate(const float *x, size_t n, ptrdiff_t ldx, const uint8_t *codes8,
                                    const uint32_t *codes32, size_t code_pitch, size_t M, size_t k, size_t dsub,
                                    const float *init, float *packed, int ordered, cudaStream_t stream);
+// sumsq64 (or nullptr): sum ||x_m||^2 per subquantizer in FP64 from launch_sumsq64, used for the loss instead of the
+// packed buffer's float slot.
 rb_status launch_kmeans_finalize(const float *packed, size_t M, size_t k, size_t dsub, uint64_t n_total,
-                                 float *centroids, float *loss, cudaStream_t stream);
+                                 float *centroids, float *loss, cudaStream_t stream, const double *sumsq64 = nullptr);
+// out[m] = sum over the n rows of ||x[:, m*dsub .. (m+1)*dsub)||^2 in FP64, fixed summation order (deterministic).
+rb_status launch_sumsq64(const float *x, size_t n, ptrdiff_t ldx, size_t M, size_t dsub, double *out, cudaStream_t stream);
 
 // vector_ops.cu — single-vector paths (latency only).
 rb_status launch_quantize_vector(const DeviceCodebook &cb, const float *projection, const float *x,

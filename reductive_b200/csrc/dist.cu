@@ -103,6 +103,7 @@ struct rb_kmeans_dist {
     float *xcol = nullptr;              // owned: [n_total, dcols] with dcols = (m_lo[rank + 1] - m_lo[rank]) * dsub
     unsigned char *codes_local = nullptr, *codes_recv = nullptr, *codes_own = nullptr;
     float *packed_own = nullptr, *loss_all = nullptr;
+    double *sumsq_own = nullptr;  // sum ||x_m||^2 of the owned subquantizers over all rows (FP64, computed once)
     int code_width = 1;
     size_t pitch_local = 0, pitch_total = 0;
     size_t m_own() const { return m_lo[c->rank + 1] - m_lo[c->rank]; }
@@ -184,6 +185,7 @@ void rb_kmeans_dist_destroy(rb_kmeans_dist *h)
     cudaFree(h->codes_own);
     cudaFree(h->packed_own);
     cudaFree(h->loss_all);
+    cudaFree(h->sumsq_own);
     delete h;
 }
 
@@ -273,7 +275,9 @@ rb_status rb_kmeans_dist_create(rb_comm *c, const float *x_local, size_t n_local
             return RB_OK;
         }();
         cudaFreeAsync(sendbuf, st);
-        return s2;
+        RB_TRY(s2);
+        RB_CUDA_TRY(cudaMalloc(&h->sumsq_own, (m_own ? m_own : 1) * sizeof(double)));
+        return launch_sumsq64(h->xcol, h->n_total, (ptrdiff_t)dcols, m_own, dsub, h->sumsq_own, st);
     };
     (void)me;
     const rb_status s = body();
@@ -328,7 +332,7 @@ rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *h, float *centroids, float *los
                                         cw == 4 ? reinterpret_cast<const uint32_t *>(h->codes_own) : nullptr, h->pitch_total,
                                         m_own, k, dsub, nullptr, h->packed_own, 1, st));
         RB_TRY(launch_kmeans_finalize(h->packed_own, m_own, k, dsub, h->n_total, centroids + h->m_lo[me] * k * dsub,
-                                      h->loss_all + h->m_lo[me], st));
+                                      h->loss_all + h->m_lo[me], st, h->sumsq_own));
     }
     // 4. everyone gets everyone's new centroids (and, when asked for, losses): one in-place all-gather when the
     //    subquantizers divide evenly, else one broadcast per rank

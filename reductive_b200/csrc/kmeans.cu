@@ -523,7 +523,7 @@ rb_status launch_ordered_fast(const float *x, size_t n, ptrdiff_t ldx, const uin
 
 __global__ void __launch_bounds__(256)
 finalize_kernel(const float *__restrict__ packed, int M, int k, int dsub, double inv_len, float *__restrict__ centroids,
-                float *__restrict__ loss)
+                float *__restrict__ loss, const double *__restrict__ sumsq64)
 {
     const int m = blockIdx.x;
     const float *gsum = packed + (size_t)m * k * dsub;
@@ -549,7 +549,9 @@ finalize_kernel(const float *__restrict__ packed, int M, int k, int dsub, double
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double s = (double)sumsq;
+        // sum ||x||^2: the deterministic FP64 value when the caller has one (training loops: x never changes, so it
+        // is computed once per run), else the packed buffer's float slot (accumulated with atomics)
+        double s = sumsq64 != nullptr ? sumsq64[m] : (double)sumsq;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
         if (s < 0.0) s = 0.0;
         loss[m] = (float)(s * inv_len);  // kmeans.rs:359: sse / (n * dsub)
@@ -655,11 +657,64 @@ rb_status launch_kmeans_accumulate(const float *x, size_t n, ptrdiff_t ldx, cons
 }
 
 rb_status launch_kmeans_finalize(const float *packed, size_t M, size_t k, size_t dsub, uint64_t n_total,
-                                 float *centroids, float *loss, cudaStream_t stream)
+                                 float *centroids, float *loss, cudaStream_t stream, const double *sumsq64)
 {
     const double len = (double)n_total * (double)dsub;
     finalize_kernel<<<(unsigned)M, 256, 0, stream>>>(packed, (int)M, (int)k, (int)dsub, len > 0 ? 1.0 / len : 0.0,
-                                                     centroids, loss);
+                                                     centroids, loss, sumsq64);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+namespace {
+
+// sum over rows of ||x_m||^2 per subquantizer in FP64 with a FIXED summation order (fixed row ranges per block, fixed
+// strides per thread, tree reduction, partials added in block order): run-to-run identical, unlike float atomics.
+constexpr int kSqBlocks = 64;
+
+__global__ void __launch_bounds__(256)
+sumsq_partial_kernel(const float *__restrict__ x, long long n, long long ldx, int dsub, double *__restrict__ partial)
+{
+    const int m = blockIdx.y;
+    const long long per = (n + kSqBlocks - 1) / kSqBlocks;
+    const long long r0 = (long long)blockIdx.x * per, r1 = min(n, r0 + per);
+    double acc = 0.0;
+    const long long total = (r1 > r0 ? r1 - r0 : 0) * dsub;
+    for (long long i = threadIdx.x; i < total; i += 256) {
+        const long long r = r0 + i / dsub;
+        const int t = (int)(i % dsub);
+        const float v = __ldg(x + r * ldx + (long long)m * dsub + t);
+        acc += (double)v * (double)v;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)m * kSqBlocks + blockIdx.x] = red[0];
+}
+
+__global__ void sumsq_final_kernel(const double *__restrict__ partial, int M, double *__restrict__ out)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double s = 0.0;
+    for (int b = 0; b < kSqBlocks; b++) s += partial[(size_t)m * kSqBlocks + b];
+    out[m] = s;
+}
+
+}  // namespace
+
+rb_status launch_sumsq64(const float *x, size_t n, ptrdiff_t ldx, size_t M, size_t dsub, double *out, cudaStream_t stream)
+{
+    if (M == 0) return RB_OK;
+    double *partial = nullptr;
+    RB_CUDA_TRY(pool_malloc((void **)&partial, M * kSqBlocks * sizeof(double), stream));
+    sumsq_partial_kernel<<<dim3(kSqBlocks, (unsigned)M), 256, 0, stream>>>(x, (long long)n, (long long)ldx, (int)dsub, partial);
+    sumsq_final_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, stream>>>(partial, (int)M, out);
+    cudaFreeAsync(partial, stream);
     RB_LAUNCH_CHECK();
     return RB_OK;
 }

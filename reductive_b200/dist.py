@@ -215,6 +215,11 @@ def kmeans_data_parallel(x_local, n_total: int, centroids, n_iterations: int, gr
     loss = torch.zeros((M,), dtype=torch.float32, device=centroids.device)
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     if distributed and mode == "chained":
+        # the relay continues chains with rb_kmeans_accumulate(packed_before): every rank checks its preconditions
+        # BEFORE the first collective, so that an unsupported shape raises everywhere instead of hanging the ranks that
+        # already wait in recv / broadcast (prefer ShardedKMeans: bit-identical as well, and it scales)
+        if k > 256 or dsub not in (1, 2, 3, 4, 5, 6, 8, 10, 12, 15, 16, 20, 30, 32) or x_local.stride(0) >= 1 << 29:
+            raise NotImplementedError(f"chained mode needs k <= 256 and an instantiated subvector width (k={k}, dsub={dsub})")
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
         ns = max(1, min(M, n_slices if n_slices is not None else min(world, 4)))

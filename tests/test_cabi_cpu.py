@@ -156,3 +156,16 @@ def test_multi_gpu_entry_points_fail_loudly_without_a_device():
     h = C.c_void_p()
     with pytest.raises(CudaError):
         check(lib.rb_comm_create(ident, 0, 1, C.byref(h)))
+
+
+def test_f64_entry_points_answer_unsupported():
+    """Pq<f64> (pq.rs:29-32): typed entry points exist and say UNSUPPORTED instead of down-converting silently."""
+    import ctypes as C
+
+    from reductive_b200._cabi import ERR_UNSUPPORTED, last_error, lib
+
+    h = C.c_void_p()
+    q = np.zeros((1, 2, 2), np.float64)
+    lib.rb_pq_create_f64.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]
+    assert lib.rb_pq_create_f64(q.ctypes.data, 1, 2, 2, None, C.byref(h)) == ERR_UNSUPPORTED
+    assert "f32 only" in last_error() and not h.value
