@@ -218,6 +218,23 @@ rb_status rb_project_rows(const float *x, size_t n, size_t d, ptrdiff_t x_row_st
                           ptrdiff_t x_col_stride, const float *r_dev, int transpose_r, float *out,
                           void *stream);
 
+/* ---- Opq / GaussianOpq training (opq.rs:46-209, gaussian_opq.rs:33-68) ------------------------------ */
+
+/* Covariance::covariance over observation axis 0 (linalg.rs:23-44) of x [n, d] (DEVICE, row stride x_row_stride):
+ * cov_out DEVICE [d, d].  RB_ERR_SHAPE for n == 0 (the reference asserts).  The d x d eigendecomposition that
+ * follows in Opq::create_projection_matrix (opq.rs:120-135) stays on host LAPACK, as in the reference. */
+rb_status rb_covariance(const float *x, size_t n, size_t d, ptrdiff_t x_row_stride, float *cov_out, void *stream);
+
+/* The device part of Opq::train_iteration (opq.rs:161-189) for all M subquantizers:
+ *   rx = x . projection (opq.rs:173, reference summation order); one kmeans_iteration per subquantizer on rx
+ *   (opq.rs:174,191-209; centroids updated in place); quantize -> reconstruct round trip with the new centroids
+ *   (opq.rs:180-182); xty_out = x^T . reconstructed (opq.rs:187).
+ * The caller takes the SVD of xty_out on host LAPACK and passes U.V^T as the next projection (opq.rs:187-188).
+ * All pointers DEVICE: x [n, d] (row stride), projection [d, d], centroids [M, k, dsub], xty_out [d, d]. */
+rb_status rb_opq_train_iteration(const float *x, size_t n, size_t d, ptrdiff_t x_row_stride, const float *projection,
+                                 float *centroids, size_t n_subquantizers, size_t n_centroids, float *xty_out,
+                                 void *stream);
+
 /* ---- A = f64 --------------------------------------------------------------------------------------- */
 
 /* Pq<A> is generic over NdFloat (pq.rs:29-32,196-203; linalg.rs:150-156); every configuration this library was built

@@ -236,6 +236,70 @@ class Oracle:
         return out, loss
 
 
+    # ---- OPQ training (test infrastructure for the "next" rows f1 / f3) ----------------------------------
+    # Composed from the C primitives above (sgemm, kmeans_iteration, quantize / reconstruct) in the reference's order;
+    # the d x d eigendecomposition / SVD go to host LAPACK through numpy as the reference's go through ndarray-linalg
+    # (opq.rs:123, opq.rs:187), so the factors agree with the reference's only up to LAPACK driver differences.
+    def covariance(self, x):
+        """Covariance::covariance, observation axis 0 (linalg.rs:23-44): mean_axis (rows added in row order, then
+        divided by n), centred copy, centred^T . (centred / (n - 1)) as one sgemm."""
+        x = np.asarray(x, np.float32)
+        n = x.shape[0]
+        assert n != 0, "Cannot compute a covariance from zero observations"
+        total = np.zeros((x.shape[1],), np.float32)
+        for row in x:  # ndarray sum_axis(Axis(0)): lane-wise running sum over the rows
+            total = total + row
+        means = total / np.float32(n)
+        centered = (x - means).astype(np.float32)
+        scaled = (centered / (np.float32(n) - np.float32(1))).astype(np.float32)
+        return self.sgemm(centered.T, scaled)
+
+    @staticmethod
+    def bucket_eigenvalues(eigenvalues, n_buckets):
+        """bucket_eigenvalues (opq.rs:212-273), written independently of the product's copy: largest eigenvalue first,
+        each into the non-full bucket with the smallest running sum of shifted logs (first bucket on ties)."""
+        ev = np.asarray(eigenvalues)
+        if ev.dtype not in (np.float32, np.float64):
+            ev = ev.astype(np.float64)
+        assert n_buckets > 0 and len(ev) >= n_buckets and len(ev) % n_buckets == 0
+        eps = np.finfo(ev.dtype).eps
+        idx = np.argsort(ev, kind="stable")  # ascending; ties keep index order like sort_unstable_by on distinct values
+        assert ev[idx[0]] >= -eps, "Bucketing is only supported for positive eigenvalues."
+        logs = np.log(ev + eps).astype(ev.dtype)
+        logs = (logs - logs.min()).astype(ev.dtype)
+        cap = len(ev) // n_buckets
+        buckets = [[] for _ in range(n_buckets)]
+        sums = np.zeros((n_buckets,), ev.dtype)
+        for i in idx[::-1]:
+            open_ = [b for b in range(n_buckets) if len(buckets[b]) < cap]
+            b = min(open_, key=lambda j: (sums[j], j))
+            buckets[b].append(int(i))
+            sums[b] = sums[b] + logs[i]
+        return buckets
+
+    def create_projection_matrix(self, x, n_subquantizers):
+        """Opq::create_projection_matrix (opq.rs:103-136)."""
+        cov = self.covariance(x)
+        values, vectors = np.linalg.eigh(cov, UPLO="U")
+        order = [i for b in self.bucket_eigenvalues(values, n_subquantizers) for i in b]
+        return np.ascontiguousarray(vectors[:, order], np.float32)
+
+    def opq_train_iteration(self, projection, centroids, x):
+        """Opq::train_iteration (opq.rs:161-189).  Returns (new projection, new centroids, X^T . Y^)."""
+        x = np.ascontiguousarray(x, np.float32)
+        r = np.ascontiguousarray(projection, np.float32)
+        c = np.array(centroids, np.float32, copy=True)
+        M, k, dsub = c.shape
+        rx = self.sgemm(x, r)                                               # opq.rs:173
+        for m in range(M):                                                  # opq.rs:174,191-209
+            c[m], _ = self.kmeans_iteration(np.ascontiguousarray(rx[:, m * dsub:(m + 1) * dsub]), c[m])
+        codes = self.quantize_batch(c, None, rx, np.uint32)                 # opq.rs:180
+        reconstructed = self.reconstruct_batch(c, None, codes)              # opq.rs:181-182
+        xty = self.sgemm(x.T, reconstructed)                                # opq.rs:187
+        u, _, vt = np.linalg.svd(xty, full_matrices=True)
+        return self.sgemm(np.ascontiguousarray(u, np.float32), np.ascontiguousarray(vt, np.float32)), c, xty
+
+
 _default = None
 
 

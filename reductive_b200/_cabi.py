@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = [
     "rb_kmeans_finalize", "rb_pq_train", "rb_project_rows",
     "rb_dist_subquantizer_range", "rb_comm_unique_id", "rb_comm_create", "rb_comm_destroy", "rb_comm_rank",
     "rb_comm_world", "rb_kmeans_dist_create", "rb_kmeans_dist_iterate", "rb_kmeans_dist_destroy", "rb_pq_train_dist",
-    "rb_pq_train_multi", "rb_pq_create_f64", "rb_pq_quantize_batch_f64", "rb_pq_reconstruct_batch_f64", "rb_pq_train_f64",
+    "rb_pq_train_multi", "rb_covariance", "rb_opq_train_iteration", "rb_pq_create_f64", "rb_pq_quantize_batch_f64", "rb_pq_reconstruct_batch_f64", "rb_pq_train_f64",
 ]
 
 
@@ -139,6 +139,8 @@ def _load() -> C.CDLL:
     lib.rb_kmeans_finalize.argtypes = [fp, sz, sz, sz, C.c_uint64, fp, fp, vp]
     lib.rb_pq_train.argtypes = [fp, sz, sz, pd, pd, sz, C.c_uint32, sz, sz, fp, fp, C.c_int, vp, C.POINTER(vp)]
     lib.rb_project_rows.argtypes = [fp, sz, sz, pd, pd, fp, C.c_int, fp, vp]
+    lib.rb_covariance.argtypes = [fp, sz, sz, pd, fp, vp]
+    lib.rb_opq_train_iteration.argtypes = [fp, sz, sz, pd, fp, fp, sz, sz, fp, vp]
     lib.rb_dist_subquantizer_range.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
     lib.rb_comm_unique_id.argtypes = [vp, sz]
     lib.rb_comm_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]

@@ -1098,6 +1098,57 @@ rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t rs, 
     return rb_pq_create(best_q.data(), M, k, dsub, nullptr, out);
 }
 
+// ---- Opq training --------------------------------------------------------------------------------------------------
+rb_status rb_covariance(const float *x, size_t n, size_t d, ptrdiff_t ldx, float *cov_out, void *stream)
+{
+    if (!x || !cov_out) return fail(RB_ERR_INVALID, "NULL argument");
+    if (n == 0) return fail(RB_ERR_SHAPE, "Cannot compute a covariance from zero observations");  // linalg.rs:24-27
+    if (d == 0 || ldx < (ptrdiff_t)d) return fail(RB_ERR_SHAPE, "bad shape (d=%zu, row stride %td)", d, ldx);
+    RB_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace means;
+    RB_TRY(means.alloc(d * sizeof(float), st));
+    RB_TRY(launch_column_means(x, n, d, ldx, means.as<float>(), st));  // linalg.rs:30
+    // centered.t().dot(&centered.map(|v| *v / normalization))  linalg.rs:31-41
+    return launch_gram(x, ldx, x, ldx, n, d, d, means.as<float>(), means.as<float>(), (float)n - 1.0f, cov_out, st);
+}
+
+rb_status rb_opq_train_iteration(const float *x, size_t n, size_t d, ptrdiff_t ldx, const float *projection, float *centroids,
+                                 size_t M, size_t k, float *xty_out, void *stream)
+{
+    if (!x || !projection || !centroids || !xty_out) return fail(RB_ERR_INVALID, "NULL argument");
+    if (M == 0 || k == 0 || d == 0 || d % M != 0 || ldx < (ptrdiff_t)d) return fail(RB_ERR_SHAPE, "bad shape");
+    if (k >= n) return fail(RB_ERR_K_MEANS_K, "Cannot pick more centroids than instances: %zu instances, %zu centroids", n, k);
+    RB_TRY(require_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t dsub = d / M;
+    Workspace rx, packed, cs, codes;
+    RB_TRY(rx.alloc(n * d * sizeof(float), st));
+    RB_TRY(packed.alloc(rb_kmeans_packed_len(M, k, dsub) * sizeof(float), st));
+    RB_TRY(launch_project(x, n, d, ldx, 1, projection, 0, rx.as<float>(), st));  // opq.rs:173
+    // one k-means step per subquantizer (opq.rs:174,191-209): kmeans.rs:319-325, all M at once
+    RB_TRY(rb_kmeans_assign_accumulate(rx.as<float>(), n, (ptrdiff_t)d, centroids, M, k, dsub, packed.as<float>(), stream));
+    RB_TRY(launch_kmeans_finalize(packed.as<float>(), M, k, dsub, n, centroids, nullptr, st));
+    // quantize -> reconstruct with the NEW centroids (opq.rs:180-182); the reconstruction reuses rx's buffer as the
+    // reference does
+    const int width = rb_kmeans_code_width(k);
+    RB_TRY(codes.alloc(n * M * (size_t)width, st));
+    RB_TRY(cs.alloc(M * k * sizeof(float), st));
+    RB_TRY(launch_centroid_norms(centroids, M * k, dsub, cs.as<float>(), st));
+    const DeviceCodebook cb{centroids, cs.as<float>(), M, k, dsub};
+    TensorOperands tc;
+    if (g_encode_algo.load() != RB_ENCODE_EXACT) RB_TRY(tc.prepare(cb, st));
+    rb_status s = encode_device(cb, &tc, rx.as<float>(), n, (ptrdiff_t)d, 0, codes.p, width, (ptrdiff_t)M, 1, st);
+    tc.release_async(st);
+    RB_TRY(s);
+    Workspace flag;
+    RB_TRY(flag.alloc(sizeof(int), st));
+    RB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+    RB_TRY(launch_gather(cb, codes.p, width, n, (ptrdiff_t)M, 1, rx.as<float>(), (ptrdiff_t)d, flag.as<int>(), st));
+    // instances.t().dot(&reconstructed)  opq.rs:187
+    return launch_gram(x, ldx, rx.as<float>(), (ptrdiff_t)d, n, d, d, nullptr, nullptr, 1.0f, xty_out, st);
+}
+
 // ---- A = f64: defined answers, no silent down-conversion (include/reductive_b200.h) -------------------------------
 static rb_status f64_unsupported(const char *what)
 {

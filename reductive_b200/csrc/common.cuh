@@ -236,6 +236,12 @@ rb_status launch_kmeans_finalize(const float *packed, size_t M, size_t k, size_t
 // out[m] = sum over the n rows of ||x[:, m*dsub .. (m+1)*dsub)||^2 in FP64, fixed summation order (deterministic).
 rb_status launch_sumsq64(const float *x, size_t n, ptrdiff_t ldx, size_t M, size_t dsub, double *out, cudaStream_t stream);
 
+// opq.cu — OPQ training helpers.  means[d] = column means of x (FP64 accumulation, fixed order);
+// out[da, db] = sum_r (a[r, :] - a_sub)^T ((b[r, :] - b_sub) / b_div)  (a_sub / b_sub may be nullptr, b_div 1).
+rb_status launch_column_means(const float *x, size_t n, size_t d, ptrdiff_t ldx, float *means, cudaStream_t stream);
+rb_status launch_gram(const float *a, ptrdiff_t lda, const float *b, ptrdiff_t ldb, size_t n, size_t da, size_t db,
+                      const float *a_sub, const float *b_sub, float b_div, float *out, cudaStream_t stream);
+
 // vector_ops.cu — single-vector paths (latency only).
 rb_status launch_quantize_vector(const DeviceCodebook &cb, const float *projection, const float *x,
                                  ptrdiff_t sx, void *codes, int code_width, ptrdiff_t cstride,

@@ -6,9 +6,10 @@ Mirror of  Opq          src/pq/opq.rs:38-209  (Ge et al., 2013; alternating k-me
 Both RETURN A `Pq` carrying the projection, so encode/decode always run through Pq (x.R before the argmin,
 pq.rs:276; R^T after the gather, pq.rs:323-326).
 
-What runs where: X.R, the k-means step, quantize and reconstruct run in this repo's kernels through the C ABI.
-The d x d eigendecomposition and SVD stay on host LAPACK (numpy), exactly as north_star scopes it; the
-covariance and X^T.Y^ Gram matrices are plain library GEMMs (torch.matmul), not hot-path kernels.
+What runs where: everything over the n rows runs in this repo's kernels through the C ABI -- the covariance
+(rb_covariance), and per training iteration X.R, the k-means step, the quantize -> reconstruct round trip and the
+Gram matrix X^T.Y^ (rb_opq_train_iteration).  Only the d x d eigendecomposition and SVD stay on host LAPACK (numpy),
+exactly as the reference does (opq.rs:123,187) and north_star scopes it.  torch is used for device memory only.
 """
 from __future__ import annotations
 
@@ -78,8 +79,10 @@ def create_projection_matrix(x, n_subquantizers: int) -> np.ndarray:
     n = x.shape[0]
     if n == 0:
         raise ReductivePanic("Cannot compute a covariance from zero observations")
-    centered = x - x.mean(dim=0, keepdim=True)
-    cov = (centered.t() @ (centered / float(n - 1))).cpu().numpy()
+    cov_dev = torch.empty((x.shape[1], x.shape[1]), dtype=torch.float32, device=x.device)
+    check(lib.rb_covariance(x.data_ptr(), n, x.shape[1], x.stride(0), cov_dev.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream))
+    cov = cov_dev.cpu().numpy()
     eigen_values, eigen_vectors = np.linalg.eigh(cov, UPLO="U")  # host LAPACK, as in the reference
     buckets = bucket_eigenvalues(eigen_values, n_subquantizers)
     order = [i for b in buckets for i in b]
@@ -115,18 +118,13 @@ class Opq(TrainPq):
             idx = torch.as_tensor(rng.choice(n, size=k, replace=False), device=x.device)
             cen[m] = rx[idx, m * dsub:(m + 1) * dsub]
         stream = torch.cuda.current_stream().cuda_stream
-        packed = torch.empty((lib.rb_kmeans_packed_len(M, k, dsub),), dtype=torch.float32, device=x.device)
+        xty = torch.empty((d, d), dtype=torch.float32, device=x.device)
         for _ in range(n_iterations):  # opq.rs:86-93 -> train_iteration opq.rs:161-189
-            rx = _project(x, projection)  # opq.rs:173
-            # one k-means step per subquantizer (opq.rs:174,191-209), all M in one launch pair
-            check(lib.rb_kmeans_assign_accumulate(rx.data_ptr(), n, rx.stride(0), cen.data_ptr(), M, k, dsub,
-                                                  packed.data_ptr(), stream))
-            check(lib.rb_kmeans_finalize(packed.data_ptr(), M, k, dsub, n, cen.data_ptr(), None, stream))
-            # quantize -> reconstruct round trip with the new centroids (opq.rs:180-182)
-            step_pq = Pq(None, cen.cpu().numpy())
-            reconstructed = step_pq.reconstruct_batch(step_pq.quantize_batch(rx, np.uint32 if k > 256 else np.uint8))
+            # device part: rx = X.R, one k-means step per subquantizer, quantize -> reconstruct, X^T.Y^
+            check(lib.rb_opq_train_iteration(x.data_ptr(), n, d, x.stride(0), projection.data_ptr(), cen.data_ptr(), M, k,
+                                             xty.data_ptr(), stream))
             # Procrustes: R = U V^T of X^T Y^ (opq.rs:187-188); d x d SVD on host LAPACK
-            u, _, vt = np.linalg.svd((x.t() @ reconstructed).cpu().numpy(), full_matrices=True)
+            u, _, vt = np.linalg.svd(xty.cpu().numpy(), full_matrices=True)
             projection = torch.from_numpy(np.ascontiguousarray(u @ vt, np.float32)).cuda()
         return Pq(projection.cpu().numpy(), cen.cpu().numpy())
 

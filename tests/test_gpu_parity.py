@@ -608,3 +608,46 @@ def test_pageable_and_pinned_host_buffers_give_the_same_codes(oracle, torch_cuda
     assert np.array_equal(codes[sample], oracle.quantize_batch(q, None, np.ascontiguousarray(x[sample]), np.uint8))
     rec = pq.reconstruct_batch(codes)
     assert np.array_equal(rec[sample], oracle.reconstruct_batch(q, None, codes[sample]))
+
+
+def test_covariance_matches_the_oracle(oracle, torch_cuda):  # linalg.rs:23-44, KAT linalg.rs:254-262
+    import ctypes as C  # noqa: F401
+
+    torch = torch_cuda
+    from reductive_b200._cabi import check, lib
+
+    def cov(x):
+        xd = torch.from_numpy(x).cuda()
+        out = torch.empty((x.shape[1], x.shape[1]), device="cuda")
+        check(lib.rb_covariance(xd.data_ptr(), x.shape[0], x.shape[1], xd.stride(0), out.data_ptr(), None))
+        return out.cpu().numpy()
+
+    assert np.array_equal(cov(np.array([[0., 2.], [1., 1.], [2., 0.]], F)), np.array([[1., -1.], [-1., 1.]], F))
+    x = normal((20_000, 96), 71) * np.linspace(0.5, 3, 96, dtype=F) + np.linspace(-2, 2, 96, dtype=F)
+    got, want = cov(x), oracle.covariance(x)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    assert np.array_equal(got, got.T) or np.abs(got - got.T).max() <= 1e-6 * np.abs(got).max()
+
+
+@pytest.mark.parametrize("n,M,k,dsub", [(6_000, 4, 16, 6), (20_000, 8, 256, 8)])
+def test_opq_train_iteration_matches_the_oracle(oracle, torch_cuda, n, M, k, dsub):
+    """Opq::train_iteration (opq.rs:161-189) from identical projection and centroids: the k-means step is bit-identical
+    (same rx: the projection kernel keeps the reference's summation order), X^T.Y^ and the new rotation agree within
+    float summation-order tolerance (1e-5 / 1e-4 relative)."""
+    torch = torch_cuda
+    from reductive_b200._cabi import check, lib
+
+    d = M * dsub
+    x = normal((n, d), 81) * np.linspace(0.3, 2, d, dtype=F)
+    r0 = oracle.create_projection_matrix(x, M)
+    rx = oracle.sgemm(x, r0)
+    c0 = rows_as_initial_centroids(rx, M, k, 82)[0]
+    want_r, want_c, want_xty = oracle.opq_train_iteration(r0, c0, x)
+    xd, rd, cd = torch.from_numpy(x).cuda(), torch.from_numpy(r0).cuda(), torch.from_numpy(c0).cuda()
+    xty = torch.empty((d, d), device="cuda")
+    check(lib.rb_opq_train_iteration(xd.data_ptr(), n, d, xd.stride(0), rd.data_ptr(), cd.data_ptr(), M, k, xty.data_ptr(), None))
+    assert np.array_equal(cd.cpu().numpy(), want_c), "k-means step differs from the oracle"
+    got_xty = xty.cpu().numpy()
+    assert np.abs(got_xty - want_xty).max() <= 1e-5 * np.abs(want_xty).max()
+    u, _, vt = np.linalg.svd(got_xty, full_matrices=True)
+    assert np.abs(u @ vt - want_r).max() <= 1e-4
