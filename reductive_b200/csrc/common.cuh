@@ -201,6 +201,16 @@ rb_status launch_encode_candidates(const DeviceCodebook &cb, const float *x, ptr
                                    const uint32_t *region_counts, uint32_t regions, uint32_t region_cap, void *codes,
                                    int code_width, ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream);
 
+// The same list for a ROTATED batch (x ~ x0 . R, every component of row i off by at most rowerr[i] + err_floor / *sx):
+// decides a pair on the approximate subvector when its candidates are further apart than the rotation error can move
+// them, else appends the row to the per-subquantizer buckets (bucket_counts[M], bucket_rows[M][n_cap]) for the exact
+// re-rotation below.
+rb_status launch_rotated_candidates(const DeviceCodebook &cb, const float *x, ptrdiff_t ldx, const uint32_t *cands,
+                                    const uint32_t *region_counts, uint32_t regions, uint32_t region_cap,
+                                    const float *rowerr, const float *sx_dev, float err_floor, uint32_t *bucket_counts,
+                                    uint32_t *bucket_rows, size_t n_cap, void *codes, int code_width, ptrdiff_t crs,
+                                    ptrdiff_t ccs, cudaStream_t stream);
+
 // Flagged rows of a ROTATED batch, bucketed per subquantizer (counts[M], rows[M][n_cap]): re-rotate the subvector
 // exactly (reference sgemm order, x0 . r) and re-decide it with the reference's expression tree.
 bool rotated_recheck_supported(const DeviceCodebook &cb, size_t d);

@@ -318,6 +318,101 @@ encode_candidates_kernel(const float *__restrict__ quantizers, const float *__re
     }
 }
 
+// Candidate lists of a ROTATED batch.  x holds the approximate rotation A of the rows (|A - T| <= ds per subvector in
+// the 2-norm, T the reference's exact rotation); the reference decides argmin_j tree(T, c_j).  With D_j = tree(A, c_j):
+//   | ||T - c_j||^2 - ||A - c_j||^2 | = |(T - A).(T + A - 2 c_j)| <= ds (2 ||A - c_j|| + ds)
+// and tree(v, c) is within e_fl = 2^-20 (||v||^2 + ||c||^2) of the real ||v - c||^2 (FP32 roundings of the norms, the
+// FMA chain and the two adds; generous), so the reference's value for j lies within
+//   E_j = ds (2 sqrt(max(D_j, 0) + e_fl) + ds) + 2 e_fl   of D_j.
+// If the best candidate b has D_b + E_b < D_j - E_j for every other candidate j, b is the reference's argmin (no tie
+// possible); otherwise the row goes to the exact re-rotation.
+template <int DSUB>
+__global__ void __launch_bounds__(256)
+rotated_candidates_kernel(const float *__restrict__ quantizers, const float *__restrict__ cs_all, int k,
+                          const float *__restrict__ x, long long ldx, const uint32_t *__restrict__ cands,
+                          const uint32_t *__restrict__ region_counts, uint32_t regions, uint32_t region_cap,
+                          const float *__restrict__ rowerr, const float *__restrict__ sx_dev, float err_floor,
+                          uint32_t *__restrict__ bucket_counts, uint32_t *__restrict__ bucket_rows, long long n_cap,
+                          void *codes, int code_width, long long crs, long long ccs)
+{
+    const float floor_err = err_floor / sx_dev[0];
+    for (uint32_t r = blockIdx.x; r < regions; r += gridDim.x) {
+      const uint32_t cnt = min(region_counts[r], region_cap);
+      for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(cands) + (size_t)r * region_cap + i);
+        const long long row = e.x;
+        const int m = (int)e.y;
+        const uint32_t ma = e.z, mb = (e.w | (e.w >> 16)) & 0xffffu;
+        const float perr = rowerr[row] + floor_err;
+        bool decided = false;
+        int best = -1;
+        if (e.z != 0xffffffffu && perr < 3.0e38f) {  // (all ones: no proof from the filter; NaN: row not rotated approximately)
+            const float *xr = x + row * ldx + (long long)m * DSUB;
+            float xv[DSUB];
+#pragma unroll
+            for (int t = 0; t < DSUB; t += 2) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(xr + t));
+                xv[t] = v.x;
+                xv[t + 1] = v.y;
+            }
+            const float xs = unrolled_sqnorm_reg<DSUB>(xv);
+            const float ds = sqrtf((float)DSUB) * perr * 1.02f;
+            const float *qm = quantizers + (size_t)m * k * DSUB;
+            const float *csg = cs_all + (size_t)m * k;
+            float d1 = __int_as_float(0x7f800000), lo2 = __int_as_float(0x7f800000);  // best D, smallest D_j - E_j of the others
+            float e1 = 0.f;
+            for (uint32_t bb = mb; bb; bb &= bb - 1) {
+                const int b = __ffs(bb) - 1;
+                for (int a = 0; a < 16; a++) {
+                    if (!((ma >> ((a >> 1) + ((a & 1) << 4))) & 1u)) continue;
+                    const int j = 16 * b + a;
+                    if (j >= k) continue;
+                    float c[DSUB];
+                    load_centroid<DSUB>(qm + (size_t)j * DSUB, c);
+                    float dp = 0.f;
+#pragma unroll
+                    for (int t = 0; t < DSUB; t++) dp = __fmaf_rn(xv[t], c[t], dp);
+                    const float csj = __ldg(csg + j);
+                    const float d = ref_distance(xs, csj, dp);
+                    const float efl = 9.5367431640625e-7f * (xs + csj);
+                    const float ej = fmaf(ds, fmaf(2.f, sqrtf(fmaxf(d, 0.f) + efl), ds), 2.f * efl);
+                    if (d < d1) {  // the previous best becomes one of the others
+                        lo2 = fminf(lo2, d1 - e1);
+                        d1 = d;
+                        e1 = ej;
+                        best = j;
+                    } else {
+                        lo2 = fminf(lo2, d - ej);
+                    }
+                }
+            }
+            decided = best >= 0 && (d1 + e1 < lo2) && (d1 == d1) && (e1 < 3.0e38f);
+        }
+        if (decided) store_code(codes, code_width, row * crs + (long long)m * ccs, (unsigned)best);
+        // Undecided pairs go to their subquantizer's bucket.  One atomic per (warp, subquantizer): the lanes that
+        // append to the same bucket elect a leader (a per-lane atomicAdd on M counters serialised the whole kernel).
+        const unsigned active = __activemask();
+        const unsigned und = __ballot_sync(active, !decided);
+        if (!decided) {
+            const unsigned peers = __match_any_sync(und, m);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&bucket_counts[m], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const uint32_t slot = base + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));  // slot < n_cap: once per (row, m)
+            // chain flags in natural order (bit a = chain a) | block flags << 16; all ones: every centroid
+            uint32_t fl = 0xffffffffu;
+            if (e.z != 0xffffffffu) {
+                uint32_t chains = 0u;
+                for (int a = 0; a < 16; a++) chains |= ((ma >> ((a >> 1) + ((a & 1) << 4))) & 1u) << a;
+                fl = chains | (mb << 16);
+            }
+            reinterpret_cast<uint2 *>(bucket_rows)[(size_t)m * (size_t)n_cap + slot] = make_uint2((uint32_t)row, fl);
+        }
+      }
+    }
+}
+
 // Flagged rows of a rotated batch (tensor rotation + tensor encode, encode_tc.cuh RotatedInput), bucketed per
 // subquantizer.  blockIdx.y = subquantizer m: the block keeps R[:, m*DSUB .. +DSUB) and the m-th codebook in shared
 // memory and walks its share of the bucket, thread = flagged row:
@@ -351,13 +446,16 @@ rotated_recheck_kernel(const uint32_t *__restrict__ counts, const uint32_t *__re
     constexpr int RPT = DSUB <= 16 ? 2 : 1;
     for (uint32_t base = blockIdx.x * (256u * RPT); base < cnt; base += gridDim.x * (256u * RPT)) {
         long long row[RPT];
+        uint32_t flags[RPT];
         const float *xr[RPT];
         bool live[RPT];
 #pragma unroll
         for (int q = 0; q < RPT; q++) {
             const uint32_t idx = base + q * 256u + threadIdx.x;
             live[q] = idx < cnt;
-            row[q] = rows[(size_t)m * (size_t)n_cap + (live[q] ? idx : base)];  // base < cnt: a valid slot
+            const uint2 ent = reinterpret_cast<const uint2 *>(rows)[(size_t)m * (size_t)n_cap + (live[q] ? idx : base)];  // base < cnt
+            row[q] = ent.x;
+            flags[q] = ent.y;
             xr[q] = x0 + row[q] * ldx0;
         }
         // One pass over the row in steps of four components (d % 4 == 0, 16-byte aligned rows:
@@ -406,20 +504,26 @@ rotated_recheck_kernel(const uint32_t *__restrict__ counts, const uint32_t *__re
             best[q] = __int_as_float(0x7f800000);
             bidx[q] = kInvalid;
         }
-#pragma unroll 2
-        for (int j = 0; j < k; j++) {
-            float c[DSUB];
-            load_centroid<DSUB>(cen + (size_t)j * DSUB, c);
-            const float csj = csm[j];
+        // only the centroids the tensor filter could not rule out (chain a = j mod 16 and block b = j / 16 both flagged;
+        // all ones: every centroid), in ascending j: strict '<' keeps the first minimum
 #pragma unroll
-            for (int q = 0; q < RPT; q++) {
-                float dp = 0.f;
+        for (int q = 0; q < RPT; q++) {
+            const uint32_t chains = flags[q] & 0xffffu, blocks = flags[q] >> 16;
+            for (uint32_t bb = blocks; bb; bb &= bb - 1) {
+                const int b = __ffs(bb) - 1;
+                for (uint32_t aa = chains; aa; aa &= aa - 1) {
+                    const int j = 16 * b + __ffs(aa) - 1;
+                    if (j >= k) continue;
+                    float c[DSUB];
+                    load_centroid<DSUB>(cen + (size_t)j * DSUB, c);
+                    float dp = 0.f;
 #pragma unroll
-                for (int t = 0; t < DSUB; t++) dp = __fmaf_rn(rx[q][t], c[t], dp);
-                const float dist = ref_distance(xs[q], csj, dp);
-                if (dist < best[q]) {
-                    best[q] = dist;
-                    bidx[q] = j;
+                    for (int t = 0; t < DSUB; t++) dp = __fmaf_rn(rx[q][t], c[t], dp);
+                    const float dist = ref_distance(xs[q], csm[j], dp);
+                    if (dist < best[q]) {
+                        best[q] = dist;
+                        bidx[q] = j;
+                    }
                 }
             }
         }
@@ -574,6 +678,33 @@ rb_status launch_encode_candidates(const DeviceCodebook &cb, const float *x, ptr
 #undef X
     default:
         set_error("candidate recheck: subvector width %zu is not instantiated", cb.dsub);
+        return RB_ERR_UNSUPPORTED;
+    }
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+rb_status launch_rotated_candidates(const DeviceCodebook &cb, const float *x, ptrdiff_t ldx, const uint32_t *cands,
+                                    const uint32_t *region_counts, uint32_t regions, uint32_t region_cap,
+                                    const float *rowerr, const float *sx_dev, float err_floor, uint32_t *bucket_counts,
+                                    uint32_t *bucket_rows, size_t n_cap, void *codes, int code_width, ptrdiff_t crs,
+                                    ptrdiff_t ccs, cudaStream_t stream)
+{
+    if (regions == 0) return RB_OK;
+    unsigned blocks = (unsigned)sm_count() * 8;
+    if (blocks > regions) blocks = regions;
+    switch (cb.dsub) {
+#define X(D)                                                                                                             \
+    case D:                                                                                                              \
+        rotated_candidates_kernel<D><<<blocks, 256, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.k, x, (long long)ldx, cands, \
+                                                                 region_counts, regions, region_cap, rowerr, sx_dev,     \
+                                                                 err_floor, bucket_counts, bucket_rows, (long long)n_cap, \
+                                                                 codes, code_width, (long long)crs, (long long)ccs);    \
+        break;
+        RB_ROT_DSUBS(X)
+#undef X
+    default:
+        set_error("rotated candidate recheck: subvector width %zu is not instantiated", cb.dsub);
         return RB_ERR_UNSUPPORTED;
     }
     RB_LAUNCH_CHECK();

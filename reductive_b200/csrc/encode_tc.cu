@@ -218,7 +218,7 @@ struct EncParams {
     float xs_limit;  // rows with ||x * scale||^2 at or above this are decided exactly
     // x is an APPROXIMATE rotation of other rows (project_tc.cu): every component of a row may be off by
     // rowerr[row] + perr_floor / *perr_sx, which widens the margin; rowerr == nullptr: x is exact
-    uint32_t *bucket_counts, *bucket_rows;  // rotated input: flagged rows per subquantizer, [M] and [M][n]
+    uint32_t *bucket_counts, *bucket_rows;  // rotated input: undecided (row, candidate flags) per subquantizer, [M] and [M][n][2]
     const float *rowerr;
     const float *perr_sx;  // device scalar: the rotation's operand scale
     float perr_floor;
@@ -635,12 +635,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                 const bool valid = grow < p.n;
                 if (valid) store_code(p.codes, p.code_width, grow * p.crs + (long long)m * p.ccs, certain ? code : 0u);
                 const bool flagged = !certain && valid;
-                if constexpr (ROT) {
-                    if (flagged) {  // a row is flagged at most once per subquantizer: slot < n
-                        const uint32_t slot = atomicAdd(&p.bucket_counts[m], 1u);
-                        p.bucket_rows[(size_t)m * (size_t)p.n + slot] = (uint32_t)grow;
-                    }
-                } else {
+                {
                     // append to this warp's private region: positions from a ballot, the count lives in a register
                     const unsigned fl = __ballot_sync(0xffffffffu, flagged);
                     if (fl != 0u) {
@@ -651,6 +646,12 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                             if (pos < p.region_cap) {
                                 uint4 *e = reinterpret_cast<uint4 *>(p.cands) + (size_t)(blockIdx.x * (4 * kSets) + warp) * p.region_cap + pos;
                                 *e = make_uint4((uint32_t)grow, (uint32_t)m, few ? ma : 0xffffffffu, few ? mb : 0xffffffffu);
+                            } else if constexpr (ROT) {
+                                // a rotated batch has no exact kernel to fall back on: straight to the re-rotation
+                                // buckets (a row is flagged at most once per subquantizer: slot < n)
+                                const uint32_t slot = atomicAdd(&p.bucket_counts[m], 1u);
+                                reinterpret_cast<uint2 *>(p.bucket_rows)[(size_t)m * (size_t)p.n + slot] =
+                                    make_uint2((uint32_t)grow, 0xffffffffu);  // (row, every centroid is a candidate)
                             } else {
                                 *p.overflow = 1u;
                             }
@@ -672,8 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                 full_ix += (uint32_t)kSets;
             }
         }
-        if constexpr (!ROT)
-            if (lane == 0) p.region_counts[blockIdx.x * (4 * kSets) + warp] = min(n_flagged, p.region_cap);
+        if (lane == 0) p.region_counts[blockIdx.x * (4 * kSets) + warp] = min(n_flagged, p.region_cap);
         RB_PH_END();
     }
 
@@ -1072,15 +1072,27 @@ rb_status launch_encode_tensor(const DeviceCodebook &cb, const TensorOperands &t
             set_error("tensor encode of a rotated batch does not cover this shape (n=%zu, d=%zu)", n, rot->d);
             return RB_ERR_UNSUPPORTED;
         }
+        // undecided pairs first go to the candidate list (per-warp regions, a quarter of the pairs a warp can meet):
+        // rotated_candidates_kernel decides them on the APPROXIMATE rotation whenever the candidates are further
+        // apart than the rotation error can move them, and only the rest is bucketed per subquantizer ([M] counters +
+        // [M][n] (row, candidate flags) pairs) for the exact re-rotation
+        const size_t n_tiles = ceil_div(n, (size_t)kTile);
+        const Plan plan = make_plan(cb.M, cb.dsub, n_tiles, device_sm_count(), 3);
+        const size_t regions = (size_t)plan.ctas * 4 * kSets;
+        const size_t region_cap = pairs_per_epilogue_warp(plan, cb.M, n_tiles) / 4 + 64;
+        const size_t counters = (cb.M + 3) / 4 * 4, head = (regions + 3) / 4 * 4;
         uint32_t *work = nullptr;
-        const size_t counters = (cb.M + 3) / 4 * 4;
-        RB_CUDA_TRY(pool_malloc((void **)&work, (counters + units) * sizeof(uint32_t), stream));
-        uint32_t *counts = work, *rows = work + counters;
+        RB_CUDA_TRY(pool_malloc((void **)&work, (counters + head + 2 * units + 4 * regions * region_cap) * sizeof(uint32_t), stream));
+        uint32_t *counts = work, *region_counts = work + counters, *cands = region_counts + head,
+                 *rows = cands + 4 * regions * region_cap;
         Undecided und;
         und.bucket_counts = counts;
         und.bucket_rows = rows;
+        und.cands = cands;
+        und.region_counts = region_counts;
+        und.region_cap = (uint32_t)region_cap;
         auto body = [&]() -> rb_status {
-            RB_CUDA_TRY(cudaMemsetAsync(counts, 0, counters * sizeof(uint32_t), stream));
+            RB_CUDA_TRY(cudaMemsetAsync(work, 0, (counters + head) * sizeof(uint32_t), stream));
             switch (cb.dsub) {
 #define X(D)                                                                                                         \
     case D:                                                                                                          \
@@ -1090,14 +1102,18 @@ rb_status launch_encode_tensor(const DeviceCodebook &cb, const TensorOperands &t
 #undef X
             default: break;
             }
+            RB_TRY(launch_rotated_candidates(cb, x, ldx, cands, region_counts, (uint32_t)regions, (uint32_t)region_cap, rot->rowerr,
+                                             rot->sx_dev, rot->err_floor, counts, rows, n, codes, code_width, crs, ccs, stream));
             if (getenv("RB_TC_STATS")) {
-                std::vector<uint32_t> h(cb.M);
-                RB_CUDA_TRY(cudaMemcpyAsync(h.data(), counts, cb.M * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+                std::vector<uint32_t> h(counters + head);
+                RB_CUDA_TRY(cudaMemcpyAsync(h.data(), work, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
                 RB_CUDA_TRY(cudaStreamSynchronize(stream));
-                size_t tot = 0;
-                for (uint32_t c : h) tot += c;
-                fprintf(stderr, "[rb tc] rotated n=%zu M=%zu dsub=%zu: %zu of %zu pairs re-rotated and re-decided exactly (%.4f%%)\n",
-                        n, cb.M, cb.dsub, tot, units, 100.0 * tot / (double)units);
+                size_t tot = 0, listed = 0;
+                for (size_t m = 0; m < cb.M; m++) tot += h[m];
+                for (size_t r = 0; r < regions; r++) listed += h[counters + r];
+                fprintf(stderr, "[rb tc] rotated n=%zu M=%zu dsub=%zu: of %zu pairs %zu undecided by the tensor filter (%.3f%%), %zu "
+                                "re-rotated exactly (%.4f%%)\n", n, cb.M, cb.dsub, units, listed, 100.0 * listed / (double)units, tot,
+                        100.0 * tot / (double)units);
             }
             return launch_rotated_recheck(cb, counts, rows, n, rot->x0, rot->ldx0, rot->r, rot->d, codes, code_width, crs, ccs,
                                           stream);
