@@ -29,6 +29,29 @@
 namespace rb {
 namespace {
 
+// Received assignment blocks -> [m_own][pitch_total] in rank (= row) order.  One launch for all ranks' blocks: block
+// (x: 16 KB piece, y: subquantizer, z: source rank).
+struct AssembleArgs {
+    const unsigned char *src[64];
+    unsigned long long src_pitch[64], bytes[64], dst_off[64];
+};
+__global__ void __launch_bounds__(256) assemble_codes_kernel(const __grid_constant__ AssembleArgs a, unsigned char *__restrict__ dst,
+                                                             unsigned long long dst_pitch)
+{
+    const int r = blockIdx.z, m = blockIdx.y;
+    const unsigned long long n = a.bytes[r];
+    const unsigned char *s = a.src[r] + (unsigned long long)m * a.src_pitch[r];
+    unsigned char *d = dst + (unsigned long long)m * dst_pitch + a.dst_off[r];
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 16384 + threadIdx.x * 16ull; i < n && i < (unsigned long long)(blockIdx.x + 1) * 16384;
+         i += 256 * 16ull) {
+        if (i + 16 <= n && ((reinterpret_cast<unsigned long long>(d + i) & 15) == 0)) {
+            *reinterpret_cast<uint4 *>(d + i) = *reinterpret_cast<const uint4 *>(s + i);  // source blocks are 16-byte aligned
+        } else {
+            for (unsigned long long j = i; j < n && j < i + 16; j++) d[j] = s[j];
+        }
+    }
+}
+
 // NCCL is resolved at run time (libnccl.so.2): a process that already carries one (torch) keeps using that copy.
 struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -321,11 +344,28 @@ rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *h, float *centroids, float *los
     }
     RB_NCCL_TRY(nccl().GroupEnd());
     // rows of all ranks in rank order = the reference's row order: [m_own][pitch_total]
-    for (int r = 0; r < W; r++)
-        if (m_own && h->n_of[r])
-            RB_CUDA_TRY(cudaMemcpy2DAsync(h->codes_own + h->row_off[r] * cw, h->pitch_total * cw, recv_at[r],
-                                          rb_kmeans_code_pitch(h->n_of[r]) * cw, h->n_of[r] * cw, m_own,
-                                          cudaMemcpyDeviceToDevice, st));
+    if (m_own && W <= 64) {
+        AssembleArgs a;
+        unsigned long long most = 0;
+        for (int r = 0; r < 64; r++) {
+            a.src[r] = r < W ? recv_at[r] : nullptr;
+            a.src_pitch[r] = r < W ? rb_kmeans_code_pitch(h->n_of[r]) * cw : 0;
+            a.bytes[r] = r < W ? h->n_of[r] * cw : 0;
+            a.dst_off[r] = r < W ? h->row_off[r] * cw : 0;
+            most = a.bytes[r] > most ? a.bytes[r] : most;
+        }
+        if (most) {
+            assemble_codes_kernel<<<dim3((unsigned)ceil_div((size_t)most, (size_t)16384), (unsigned)m_own, (unsigned)W), 256, 0, st>>>(
+                a, h->codes_own, h->pitch_total * cw);
+            RB_LAUNCH_CHECK();
+        }
+    } else {
+        for (int r = 0; r < W; r++)
+            if (m_own && h->n_of[r])
+                RB_CUDA_TRY(cudaMemcpy2DAsync(h->codes_own + h->row_off[r] * cw, h->pitch_total * cw, recv_at[r],
+                                              rb_kmeans_code_pitch(h->n_of[r]) * cw, h->n_of[r] * cw, m_own,
+                                              cudaMemcpyDeviceToDevice, st));
+    }
     // 3. update_centroids of the owned subquantizers over ALL rows, in row order (kmeans.rs:166-198)
     if (m_own) {
         RB_TRY(launch_kmeans_accumulate(h->xcol, h->n_total, (ptrdiff_t)dcols, cw == 1 ? h->codes_own : nullptr,

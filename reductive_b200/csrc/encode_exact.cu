@@ -665,12 +665,11 @@ rb_status launch_encode_candidates(const DeviceCodebook &cb, const float *x, ptr
                                    int code_width, ptrdiff_t crs, ptrdiff_t ccs, cudaStream_t stream)
 {
     if (regions == 0) return RB_OK;
-    unsigned blocks = (unsigned)sm_count() * 8;
-    if (blocks > regions) blocks = regions;
+    const unsigned blocks = regions;  // one block per region (about 12 per SM): an even share for every block
     switch (cb.dsub) {
 #define X(D)                                                                                                             \
     case D:                                                                                                              \
-        encode_candidates_kernel<D><<<blocks, 256, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.k, x, (long long)ldx, cands, \
+        encode_candidates_kernel<D><<<blocks, 128, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.k, x, (long long)ldx, cands, \
                                                                 region_counts, regions, region_cap, codes, code_width,  \
                                                                 (long long)crs, (long long)ccs);                        \
         break;
@@ -691,12 +690,11 @@ rb_status launch_rotated_candidates(const DeviceCodebook &cb, const float *x, pt
                                     ptrdiff_t ccs, cudaStream_t stream)
 {
     if (regions == 0) return RB_OK;
-    unsigned blocks = (unsigned)sm_count() * 8;
-    if (blocks > regions) blocks = regions;
+    const unsigned blocks = regions;
     switch (cb.dsub) {
 #define X(D)                                                                                                             \
     case D:                                                                                                              \
-        rotated_candidates_kernel<D><<<blocks, 256, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.k, x, (long long)ldx, cands, \
+        rotated_candidates_kernel<D><<<blocks, 128, 0, stream>>>(cb.quantizers, cb.cs, (int)cb.k, x, (long long)ldx, cands, \
                                                                  region_counts, regions, region_cap, rowerr, sx_dev,     \
                                                                  err_floor, bucket_counts, bucket_rows, (long long)n_cap, \
                                                                  codes, code_width, (long long)crs, (long long)ccs);    \
