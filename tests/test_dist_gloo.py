@@ -167,3 +167,63 @@ def test_chained_data_parallel_kmeans_is_bit_identical_to_one_process(oracle, wo
     want_q, _ = oracle.train_pq(x, M, 3, iters, 1, init)
     for r in range(world):  # replicated and bit-identical to the oracle's sequential k-means
         assert np.array_equal(got[r].view(np.uint32), want_q.view(np.uint32)), r
+
+
+# ---- the sharded mode's protocol (csrc/dist.cu) modelled over gloo ------------------------------------------
+def _sharded_worker(rank, world, port, n, M, k, dsub, iters, q):
+    """Same exchanges as rb_kmeans_dist_create / _iterate, with the oracle's CPU routines as the per-rank compute:
+    column slices of x once, per iteration the assignments (to the owner of each subquantizer) and the centroids."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from reductive_b200.dist import shard_rows, subquantizer_range
+
+    o = orc.get()
+    x = normal((n, M * dsub), 21)
+    cen = rows_as_initial_centroids(x, M, k, 22)[0].copy()
+    lo, hi = shard_rows(n, rank, world)
+    x_local = np.ascontiguousarray(x[lo:hi])
+    ranges = [subquantizer_range(M, r, world) for r in range(world)]
+    m0, m1 = ranges[rank]
+    # create: everyone's rows of my columns, in rank (= row) order
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [np.ascontiguousarray(x_local[:, a * dsub:b * dsub]) for a, b in ranges])
+    xcol = np.concatenate([g[rank] for g in gathered], axis=0) if m1 > m0 else np.zeros((n, 0), np.float32)
+    for _ in range(iters):
+        codes_local = np.stack([o.cluster_assignments(cen[m], np.ascontiguousarray(x_local[:, m * dsub:(m + 1) * dsub]))
+                                for m in range(M)]).astype(np.uint8)          # [M, n_local]: assignment by rows
+        dist.all_gather_object(gathered, [codes_local[a:b] for a, b in ranges])
+        codes_own = np.concatenate([g[rank] for g in gathered], axis=1)       # [m_own, n]: all rows, row order
+        for j, m in enumerate(range(m0, m1)):                                  # ordered update by subquantizers
+            cen[m] = o.update_centroids(cen[m], np.ascontiguousarray(xcol[:, j * dsub:(j + 1) * dsub]),
+                                        codes_own[j].astype(np.uint64))
+        dist.all_gather_object(gathered, cen[m0:m1])
+        cen = np.concatenate([g for g in gathered if len(g)], axis=0)
+    if rank == 0:
+        q.put(cen)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,M", [(2, 3), (3, 4), (3, 2)])
+def test_sharded_kmeans_protocol_is_bit_identical_to_one_process(oracle, world, M):
+    """Assignment sharded by rows + update sharded by subquantizers reproduces the sequential run bit for bit
+    (src/kmeans.rs:185-189 adds every cluster's rows in row order), including uneven row blocks and ranks that own no
+    subquantizer."""
+    n, k, dsub, iters = 601, 8, 4, 4
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, n, M, k, dsub, iters, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    cen = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+    x = normal((n, M * dsub), 21)
+    init = rows_as_initial_centroids(x, M, k, 22)
+    want, _ = oracle.train_pq(x, M, 3, iters, 1, init, n_threads=2)
+    assert np.array_equal(cen.view(np.int32), want.view(np.int32))
