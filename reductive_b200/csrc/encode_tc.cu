@@ -555,24 +555,25 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                 //                    kept as (minimum over even j, minimum over odd j)
                 uint32_t A[8], B[16];
                 uint32_t v0[32], v1[32];
-                // The accumulator is held for two load round trips and two of the four reductions only: the first two
-                // loads are issued together, the last two as soon as their registers are free, and the accumulator is
-                // released (and the next MMA issued) BEFORE the last two reductions.
                 tmem_ld32_pack16(taddr, v0);
-                tmem_ld32_pack16(taddr + 64, v1);
                 tmem_wait_ld(v0);
-                tmem_wait_ld(v1);
+                tmem_ld32_pack16(taddr + 64, v1);
 #pragma unroll
                 for (int gq = 0; gq < 4; gq++) B[gq] = hmin8(v0 + 8 * gq);
 #pragma unroll
                 for (int a = 0; a < 8; a++) A[a] = hmin3(hmin2(v0[a], v0[8 + a]), v0[16 + a], v0[24 + a]);
+                tmem_wait_ld(v1);
                 tmem_ld32_pack16(taddr + 128, v0);
 #pragma unroll
                 for (int gq = 0; gq < 4; gq++) B[4 + gq] = hmin8(v1 + 8 * gq);
 #pragma unroll
                 for (int a = 0; a < 8; a++) A[a] = hmin3(hmin3(A[a], v1[a], v1[8 + a]), v1[16 + a], v1[24 + a]);
-                tmem_ld32_pack16(taddr + 192, v1);
                 tmem_wait_ld(v0);
+                tmem_ld32_pack16(taddr + 192, v1);
+#pragma unroll
+                for (int gq = 0; gq < 4; gq++) B[8 + gq] = hmin8(v0 + 8 * gq);
+#pragma unroll
+                for (int a = 0; a < 8; a++) A[a] = hmin3(hmin3(A[a], v0[a], v0[8 + a]), v0[16 + a], v0[24 + a]);
                 tmem_wait_ld(v1);
                 // the accumulator is free again
                 tc_fence_before();
@@ -593,10 +594,6 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(const __grid_con
                     i_ml += (uint32_t)kSets;
                     while (i_ml >= (uint32_t)gm_cur) i_ml -= (uint32_t)gm_cur;
                 }
-#pragma unroll
-                for (int gq = 0; gq < 4; gq++) B[8 + gq] = hmin8(v0 + 8 * gq);
-#pragma unroll
-                for (int a = 0; a < 8; a++) A[a] = hmin3(hmin3(A[a], v0[a], v0[8 + a]), v0[16 + a], v0[24 + a]);
 #pragma unroll
                 for (int gq = 0; gq < 4; gq++) B[12 + gq] = hmin8(v1 + 8 * gq);
 #pragma unroll
