@@ -322,16 +322,11 @@ def run_ours(args) -> None:
         dist.all_reduce(cen0, op=dist.ReduceOp.SUM)  # every entry comes from exactly one rank: exact
     loss3 = torch.zeros((M3,), device=dev)
     log("k-means: initial centroids ready")
-    if world > 1:
-        comm = Comm()
-        km = ShardedKMeans(comm, x3, M3, K_CENTROIDS, dsub3)
-        step3 = lambda c, l=None: km.iterate(c, l)  # noqa: E731
-    else:
-        packed3 = torch.empty((M3 * K_CENTROIDS * dsub3 + M3 * K_CENTROIDS + M3,), device=dev)
-
-        def step3(c, l=None):
-            cuda_local_step(x3, c, packed3)
-            cuda_finalize(packed3, n3, c, l)
+    # the training-loop state of the library (csrc/dist.cu; a single rank exchanges nothing): both layouts of the rows,
+    # FP64 sum of squares, streaming ordered update
+    comm = Comm() if world > 1 else Comm(rank=0, world=1)
+    km = ShardedKMeans(comm, x3, M3, K_CENTROIDS, dsub3)
+    step3 = lambda c, l=None: km.iterate(c, l)  # noqa: E731
     cen3 = cen0.clone()
     for _ in range(2):
         step3(cen3)
@@ -352,8 +347,8 @@ def run_ours(args) -> None:
     it_bytes = n3 * (2 * 4 * M3 * dsub3 + 2 * M3)
     it_gbs = it_bytes / (it_ms * 1e-3) / 1e9 / world
     bit_identical = None
+    km.close()
     if world > 1:
-        km.close()
         same_everywhere = cen3.view(torch.int32).clone()
         dist.broadcast(same_everywhere, src=0)
         agree = torch.tensor([int(torch.equal(same_everywhere, cen3.view(torch.int32)))], device=dev)
@@ -368,14 +363,23 @@ def run_ours(args) -> None:
             bit_identical = bool(torch.equal(ref.view(torch.int32), cen3.view(torch.int32))) and bool(agree.item())
             del x_all
         barrier()  # every rank is done with the communicator before any rank tears its side down
-        comm.close()
+    else:  # one GPU: against the stateless entry points (sort + chain kernels on the row-major rows)
+        ref = cen0.clone()
+        packed3 = torch.empty((M3 * K_CENTROIDS * dsub3 + M3 * K_CENTROIDS + M3,), device=dev)
+        for _ in range(iters3):
+            cuda_local_step(x3, ref, packed3)
+            cuda_finalize(packed3, n3, ref, None)
+        bit_identical = bool(torch.equal(ref.view(torch.int32), cen3.view(torch.int32)))
+    comm.close()
     extra["pq_kmeans"] = {
         "workload": f"C3: Pq k-means 1M x 768 f32, 96 x 256 centroids, {iters3} iterations from SURVEY 8d's row picks, "
                     f"rows sharded over {world} GPU(s)",
         "sec_per_iter": it_ms * 1e-3, "iters_timed": iters3,
         "mode": "sharded: assignment by rows, ordered update by subquantizers (NCCL inside the C++ library)" if world > 1
-                else "one GPU: assignment + ordered update (reference summation order)",
-        "bit_identical_to_1gpu": bit_identical if world > 1 else True,
+                else "one GPU: assignment + streaming ordered update (reference summation order)",
+        "bit_identical_to_1gpu": bit_identical,
+        "bit_identity_checked_against": "a one-GPU run of the same rows through rb_kmeans_assign_accumulate / rb_kmeans_finalize "
+                                        "(sort + chain kernels)",
         "exchange_bytes_per_iter": (n3 * M3 + 4 * M3 * K_CENTROIDS * dsub3 * world) if world > 1 else 0,
         "roofline": {"bound": "hbm", "achieved": it_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s per GPU",
                      "frac": it_gbs / peaks["hbm_gbs"],

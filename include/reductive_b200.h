@@ -90,9 +90,11 @@ rb_status rb_release_scratch(void);
 /* Process-wide choice of the rotation kernel (rb_project_algo). */
 rb_status rb_set_project_algo(int algo);
 
-/* Centroid-update summation order of the k-means entry points (process-wide).  ordered != 0 (default):
+/* Centroid-update summation order of the k-means entry points (process-wide).  ordered != 0 (default 1):
  * rows of a cluster are added sequentially in row order exactly like kmeans.rs:185-189, so sums are
- * bit-identical to the reference's on one GPU; 0: shared-memory atomics, order unspecified. */
+ * bit-identical to the reference's (1, 2: stable sort + chain kernels; 3: the training loops stream
+ * subquantizer-major slabs instead -- the same bits, measured slower, kept as an experiment); 0: shared-memory
+ * atomics, order unspecified. */
 rb_status rb_set_kmeans_update(int ordered);
 
 /* ---- Pq construction and accessors ----------------------------------------------------------- */

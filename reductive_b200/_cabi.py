@@ -205,6 +205,7 @@ def set_project_algo(algo: int) -> None:
     check(lib.rb_set_project_algo(algo))
 
 
-def set_kmeans_update(ordered: bool) -> None:
-    """ordered=True (default): reference summation order, bit-exact sums on one GPU; False: atomics."""
-    check(lib.rb_set_kmeans_update(1 if ordered else 0))
+def set_kmeans_update(ordered) -> None:
+    """True / 1 (default): reference summation order, bit-exact sums (stable sort + chain kernels); 3: the same bits
+    from the streaming slab kernel in training loops (experimental, slower); False / 0: atomics."""
+    check(lib.rb_set_kmeans_update(int(ordered)))

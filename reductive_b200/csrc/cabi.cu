@@ -33,6 +33,9 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+bool kmeans_stream_enabled() { return g_kmeans_ordered.load() == 3; }
+int kmeans_update_mode() { return g_kmeans_ordered.load(); }
+
 bool debug_sync_enabled()
 {
     static const bool on = getenv("RB_DEBUG_SYNC") != nullptr;
@@ -650,7 +653,8 @@ rb_status rb_set_project_algo(int algo)
 
 rb_status rb_set_kmeans_update(int ordered)
 {
-    g_kmeans_ordered.store(ordered ? 1 : 0);
+    if (ordered < 0 || ordered > 3) return fail(RB_ERR_INVALID, "kmeans update mode must be 0, 1, 2 or 3");
+    g_kmeans_ordered.store(ordered);
     return RB_OK;
 }
 
@@ -1066,22 +1070,30 @@ rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t rs, 
         ldx = (ptrdiff_t)d;
     }
 
-    Workspace cen, packed, loss_dev, sumsq;
-    // sum ||x||^2 per subquantizer once (the instances never change): FP64, fixed order, so that the losses that rank
-    // the attempts (pq.rs:183-187) are run-to-run identical and free of float-atomic cancellation noise
-    RB_TRY(sumsq.alloc(M * sizeof(double), st));
-    RB_TRY(launch_sumsq64(x, n, ldx, M, dsub, sumsq.as<double>(), st));
+    // The loop runs on the single-rank form of the sharded k-means state (csrc/dist.cu): it keeps sum ||x||^2 per
+    // subquantizer in FP64 (fixed order, computed once: the instances never change) so that the losses that rank the
+    // attempts (pq.rs:183-187) are run-to-run identical, and the subquantizer-major slabs the streaming update reads.
+    rb_comm *self = nullptr;
+    rb_kmeans_dist *state = nullptr;
+    RB_TRY(rb_comm_create(nullptr, 0, 1, &self));
+    struct Cleanup {
+        rb_comm *&c;
+        rb_kmeans_dist *&s;
+        ~Cleanup()
+        {
+            rb_kmeans_dist_destroy(s);
+            rb_comm_destroy(c);
+        }
+    } cleanup{self, state};
+    RB_TRY(rb_kmeans_dist_create(self, x, n, ldx, M, k, dsub, stream, &state));
+    Workspace cen, loss_dev;
     RB_TRY(cen.alloc(qn * sizeof(float), st));
-    RB_TRY(packed.alloc(rb_kmeans_packed_len(M, k, dsub) * sizeof(float), st));
     RB_TRY(loss_dev.alloc(M * sizeof(float), st));
     std::vector<float> best_q(qn), cand_q(qn), best_loss(M, 0.f), cand_loss(M, 0.f);
     for (size_t a = 0; a < n_attempts; a++) {  // pq.rs:168-183, all subquantizers advance together
         RB_CUDA_TRY(cudaMemcpyAsync(cen.p, initial + a * qn, qn * sizeof(float), cudaMemcpyHostToDevice, st));
-        for (size_t it = 0; it < n_iterations; it++) {  // kmeans.rs:279-284
-            RB_TRY(rb_kmeans_assign_accumulate(x, n, ldx, cen.as<float>(), M, k, dsub, packed.as<float>(), st));
-            RB_TRY(launch_kmeans_finalize(packed.as<float>(), M, k, dsub, n, cen.as<float>(),
-                                          it + 1 == n_iterations ? loss_dev.as<float>() : nullptr, st, sumsq.as<double>()));
-        }
+        for (size_t it = 0; it < n_iterations; it++)  // kmeans.rs:279-284
+            RB_TRY(rb_kmeans_dist_iterate(state, cen.as<float>(), it + 1 == n_iterations ? loss_dev.as<float>() : nullptr, stream));
         RB_CUDA_TRY(cudaMemcpyAsync(cand_q.data(), cen.p, qn * sizeof(float), cudaMemcpyDeviceToHost, st));
         RB_CUDA_TRY(cudaMemcpyAsync(cand_loss.data(), loss_dev.p, M * sizeof(float), cudaMemcpyDeviceToHost, st));
         RB_CUDA_TRY(cudaStreamSynchronize(st));

@@ -252,6 +252,16 @@ rb_status launch_column_means(const float *x, size_t n, size_t d, ptrdiff_t ldx,
 rb_status launch_gram(const float *a, ptrdiff_t lda, const float *b, ptrdiff_t ldb, size_t n, size_t da, size_t db,
                       const float *a_sub, const float *b_sub, float b_div, float *out, cudaStream_t stream);
 
+// Streaming ordered update for training loops (kmeans.cu): x laid out once as subquantizer-major slabs
+// (slab_floats(n, d) floats), then per iteration one pass that streams the slabs; sums bit-identical to the chain path.
+bool stream_update_supported(size_t k, size_t dsub);
+bool kmeans_stream_enabled();  // rb_set_kmeans_update(3): training loops use the streaming update (experimental, slower)
+int kmeans_update_mode();      // 0: shared-memory atomics, 1 / 2: ordered (sort + chains), 3: ordered, streaming slabs
+size_t slab_floats(size_t n, size_t d);
+rb_status launch_build_slabs(const float *x, size_t n, ptrdiff_t ldx, size_t M, size_t dsub, float *slabs, cudaStream_t stream);
+rb_status launch_ordered_stream(const float *slabs, size_t n, const uint8_t *codes, size_t code_pitch, size_t M, size_t k,
+                                size_t dsub, float *packed, cudaStream_t stream);
+
 // vector_ops.cu — single-vector paths (latency only).
 rb_status launch_quantize_vector(const DeviceCodebook &cb, const float *projection, const float *x,
                                  ptrdiff_t sx, void *codes, int code_width, ptrdiff_t cstride,

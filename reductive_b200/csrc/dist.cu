@@ -127,6 +127,7 @@ struct rb_kmeans_dist {
     unsigned char *codes_local = nullptr, *codes_recv = nullptr, *codes_own = nullptr;
     float *packed_own = nullptr, *loss_all = nullptr;
     double *sumsq_own = nullptr;  // sum ||x_m||^2 of the owned subquantizers over all rows (FP64, computed once)
+    float *slabs = nullptr;       // streaming update: the owned columns as subquantizer-major slabs (then xcol is dropped)
     int code_width = 1;
     size_t pitch_local = 0, pitch_total = 0;
     size_t m_own() const { return m_lo[c->rank + 1] - m_lo[c->rank]; }
@@ -162,11 +163,10 @@ rb_status rb_comm_create(const void *id, int rank, int world, rb_comm **out)
 {
     if (!out) return RB_ERR_INVALID;
     *out = nullptr;
-    if (!id || world <= 0 || rank < 0 || rank >= world) {
+    if ((!id && world != 1) || world <= 0 || rank < 0 || rank >= world) {
         set_error("bad communicator arguments (rank %d of %d)", rank, world);
         return RB_ERR_INVALID;
     }
-    RB_TRY(require_nccl());
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
         (void)cudaGetLastError();
@@ -177,6 +177,14 @@ rb_status rb_comm_create(const void *id, int rank, int world, rb_comm **out)
     c->rank = rank;
     c->world = world;
     cudaGetDevice(&c->device);
+    if (world == 1) {  // a single rank exchanges nothing: no NCCL communicator behind it
+        *out = c;
+        return RB_OK;
+    }
+    if (require_nccl() != RB_OK) {
+        delete c;
+        return RB_ERR_NCCL;
+    }
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof(uid));
     const ncclResult_t r = nccl().CommInitRank(&c->comm, world, uid, rank);
@@ -209,6 +217,7 @@ void rb_kmeans_dist_destroy(rb_kmeans_dist *h)
     cudaFree(h->packed_own);
     cudaFree(h->loss_all);
     cudaFree(h->sumsq_own);
+    cudaFree(h->slabs);
     delete h;
 }
 
@@ -239,19 +248,24 @@ rb_status rb_kmeans_dist_create(rb_comm *c, const float *x_local, size_t n_local
     for (int r = 0; r <= W; r++) h->m_lo[r] = M * (size_t)r / (size_t)W;
     auto body = [&]() -> rb_status {
         // row counts of every rank (rank r's rows follow rank r - 1's in the reference's row order)
-        unsigned long long *cnt_dev = nullptr;
-        RB_CUDA_TRY(cudaMalloc(&cnt_dev, (size_t)(W + 1) * sizeof(unsigned long long)));
-        const unsigned long long mine = n_local;
         std::vector<unsigned long long> cnt(W);
-        rb_status s = [&]() -> rb_status {
-            RB_CUDA_TRY(cudaMemcpyAsync(cnt_dev + W, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
-            RB_NCCL_TRY(nccl().AllGather(cnt_dev + W, cnt_dev, 1, ncclUint64, c->comm, st));
-            RB_CUDA_TRY(cudaMemcpyAsync(cnt.data(), cnt_dev, (size_t)W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            RB_CUDA_TRY(cudaStreamSynchronize(st));
-            return RB_OK;
-        }();
-        cudaFree(cnt_dev);
-        RB_TRY(s);
+        if (W == 1) {
+            cnt[0] = n_local;
+        } else {
+            RB_TRY(require_nccl());
+            unsigned long long *cnt_dev = nullptr;
+            RB_CUDA_TRY(cudaMalloc(&cnt_dev, (size_t)(W + 1) * sizeof(unsigned long long)));
+            const unsigned long long mine = n_local;
+            rb_status s = [&]() -> rb_status {
+                RB_CUDA_TRY(cudaMemcpyAsync(cnt_dev + W, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+                RB_NCCL_TRY(nccl().AllGather(cnt_dev + W, cnt_dev, 1, ncclUint64, c->comm, st));
+                RB_CUDA_TRY(cudaMemcpyAsync(cnt.data(), cnt_dev, (size_t)W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                RB_CUDA_TRY(cudaStreamSynchronize(st));
+                return RB_OK;
+            }();
+            cudaFree(cnt_dev);
+            RB_TRY(s);
+        }
         h->n_of.resize(W);
         h->row_off.resize(W + 1);
         h->row_off[0] = 0;
@@ -265,13 +279,24 @@ rb_status rb_kmeans_dist_create(rb_comm *c, const float *x_local, size_t n_local
         const size_t m_own = h->m_own(), dcols = m_own * dsub, cw = (size_t)h->code_width;
         size_t recv_bytes = 0;
         for (int r = 0; r < W; r++) recv_bytes += m_own * rb_kmeans_code_pitch(h->n_of[r]) * cw;
-        RB_CUDA_TRY(cudaMalloc(&h->xcol, (h->n_total * dcols + 4) * sizeof(float)));
+        const bool stream_upd = kmeans_stream_enabled() && cw == 1 && stream_update_supported(k, dsub);
         RB_CUDA_TRY(cudaMalloc(&h->codes_local, M * h->pitch_local * cw + 16));
+        RB_CUDA_TRY(cudaMalloc(&h->packed_own, (rb_kmeans_packed_len(m_own ? m_own : 1, k, dsub)) * sizeof(float)));
+        RB_CUDA_TRY(cudaMalloc(&h->loss_all, M * sizeof(float)));
+        RB_CUDA_TRY(cudaMalloc(&h->sumsq_own, (m_own ? m_own : 1) * sizeof(double)));
+        if (W == 1) {
+            // one rank: nothing to exchange; the rows stay where they are (row-major), slabs are built from them
+            RB_TRY(launch_sumsq64(x_local, n_local, x_row_stride, M, dsub, h->sumsq_own, st));
+            if (stream_upd) {
+                RB_CUDA_TRY(cudaMalloc(&h->slabs, slab_floats(n_local, h->d) * sizeof(float)));
+                RB_TRY(launch_build_slabs(x_local, n_local, x_row_stride, M, dsub, h->slabs, st));
+            }
+            return RB_OK;
+        }
+        RB_CUDA_TRY(cudaMalloc(&h->xcol, (h->n_total * dcols + 4) * sizeof(float)));
         RB_CUDA_TRY(cudaMalloc(&h->codes_recv, recv_bytes + 16));
         RB_CUDA_TRY(cudaMalloc(&h->codes_own, m_own * h->pitch_total * cw + 16));
         RB_CUDA_TRY(cudaMemsetAsync(h->codes_own, 0, m_own * h->pitch_total * cw + 16, st));
-        RB_CUDA_TRY(cudaMalloc(&h->packed_own, (rb_kmeans_packed_len(m_own ? m_own : 1, k, dsub)) * sizeof(float)));
-        RB_CUDA_TRY(cudaMalloc(&h->loss_all, M * sizeof(float)));
         // one-time all-to-all of the training matrix: rank s receives x[rows of r, columns of s] from every r
         float *sendbuf = nullptr;
         RB_CUDA_TRY(pool_malloc((void **)&sendbuf, (n_local * h->d + 4) * sizeof(float), st));
@@ -299,8 +324,15 @@ rb_status rb_kmeans_dist_create(rb_comm *c, const float *x_local, size_t n_local
         }();
         cudaFreeAsync(sendbuf, st);
         RB_TRY(s2);
-        RB_CUDA_TRY(cudaMalloc(&h->sumsq_own, (m_own ? m_own : 1) * sizeof(double)));
-        return launch_sumsq64(h->xcol, h->n_total, (ptrdiff_t)dcols, m_own, dsub, h->sumsq_own, st);
+        RB_TRY(launch_sumsq64(h->xcol, h->n_total, (ptrdiff_t)dcols, m_own, dsub, h->sumsq_own, st));
+        if (stream_upd && m_own) {  // the update streams slabs: build them once, the column shard is not needed again
+            RB_CUDA_TRY(cudaMalloc(&h->slabs, slab_floats(h->n_total, dcols) * sizeof(float)));
+            RB_TRY(launch_build_slabs(h->xcol, h->n_total, (ptrdiff_t)dcols, m_own, dsub, h->slabs, st));
+            RB_CUDA_TRY(cudaStreamSynchronize(st));
+            cudaFree(h->xcol);
+            h->xcol = nullptr;
+        }
+        return RB_OK;
     };
     (void)me;
     const rb_status s = body();
@@ -326,6 +358,16 @@ rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *h, float *centroids, float *los
     // 1. cluster_assignments of the local rows against all M codebooks (kmeans.rs:319)
     RB_TRY(rb_kmeans_assign(h->x_local, h->n_local, h->ldx, centroids, M, k, dsub, h->codes_local, stream));
     // 2. the assignments of subquantizers [m_lo[s], m_lo[s+1]) go to rank s (column-major blocks are contiguous)
+    const unsigned char *codes_own = h->codes_own;
+    size_t pitch_own = h->pitch_total;
+    const float *x_own = h->xcol;
+    ptrdiff_t ld_own = (ptrdiff_t)dcols;
+    if (W == 1) {  // one rank owns everything: the local assignments ARE the owned ones
+        codes_own = h->codes_local;
+        pitch_own = h->pitch_local;
+        x_own = h->x_local;
+        ld_own = h->ldx;
+    } else {
     std::vector<unsigned char *> recv_at(W);
     {
         size_t off = 0;
@@ -366,18 +408,24 @@ rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *h, float *centroids, float *los
                                               rb_kmeans_code_pitch(h->n_of[r]) * cw, h->n_of[r] * cw, m_own,
                                               cudaMemcpyDeviceToDevice, st));
     }
+    }
     // 3. update_centroids of the owned subquantizers over ALL rows, in row order (kmeans.rs:166-198)
     if (m_own) {
-        RB_TRY(launch_kmeans_accumulate(h->xcol, h->n_total, (ptrdiff_t)dcols, cw == 1 ? h->codes_own : nullptr,
-                                        cw == 4 ? reinterpret_cast<const uint32_t *>(h->codes_own) : nullptr, h->pitch_total,
-                                        m_own, k, dsub, nullptr, h->packed_own, 1, st));
+        if (h->slabs)
+            RB_TRY(launch_ordered_stream(h->slabs, h->n_total, codes_own, pitch_own, m_own, k, dsub, h->packed_own, st));
+        else
+            RB_TRY(launch_kmeans_accumulate(x_own, h->n_total, ld_own, cw == 1 ? codes_own : nullptr,
+                                            cw == 4 ? reinterpret_cast<const uint32_t *>(codes_own) : nullptr, pitch_own, m_own, k,
+                                            dsub, nullptr, h->packed_own, kmeans_update_mode() != 0 ? 1 : 0, st));
         RB_TRY(launch_kmeans_finalize(h->packed_own, m_own, k, dsub, h->n_total, centroids + h->m_lo[me] * k * dsub,
                                       h->loss_all + h->m_lo[me], st, h->sumsq_own));
     }
     // 4. everyone gets everyone's new centroids (and, when asked for, losses): one in-place all-gather when the
     //    subquantizers divide evenly, else one broadcast per rank
     const bool even = M % (size_t)W == 0;
-    if (even) {
+    if (W == 1) {
+        // nothing to exchange
+    } else if (even) {
         RB_NCCL_TRY(nccl().AllGather(centroids + h->m_lo[me] * k * dsub, centroids, m_own * k * dsub, ncclFloat, c->comm, st));
         if (loss_or_null) RB_NCCL_TRY(nccl().AllGather(h->loss_all + h->m_lo[me], h->loss_all, m_own, ncclFloat, c->comm, st));
     } else {

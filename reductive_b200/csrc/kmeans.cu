@@ -28,6 +28,7 @@
 // chains begun on the preceding rank, which keeps multi-GPU training bit-exact (dist.py mode="chained").
 // Counts follow the reference's f32 `+= 1.0` (exact to 2^24 per cluster, kmeans.rs:188).
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace rb {
 
@@ -715,6 +716,224 @@ rb_status launch_sumsq64(const float *x, size_t n, ptrdiff_t ldx, size_t M, size
     sumsq_partial_kernel<<<dim3(kSqBlocks, (unsigned)M), 256, 0, stream>>>(x, (long long)n, (long long)ldx, (int)dsub, partial);
     sumsq_final_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, stream>>>(partial, (int)M, out);
     cudaFreeAsync(partial, stream);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+
+// =========================================================================================================
+// Streaming ordered update (training loops: the instances persist across iterations)
+// =========================================================================================================
+// The chain kernels above gather 32-byte pieces of x through L2 at ~2 TB/s whatever the prefetch depth.  A training
+// loop reads the same x every iteration, so it pays to lay x out ONCE as subquantizer-major slabs
+//   slabs[m][row][dsub]   (row pitch dsub floats, slab pitch n_pad * dsub floats, n_pad = n rounded up to 16)
+// and to STREAM them: one CTA per (subquantizer, group of KC clusters) walks the rows in order in tiles of kStreamRows,
+// double-buffered in shared memory by cp.async.bulk (contiguous copies: full HBM efficiency); per tile
+//   route:  every thread takes rows of the tile and sets bit (row) of its cluster's bitmap (shared-memory atomicOr)
+//           plus the word's bit in the cluster's summary word;
+//   chains: lanes = (cluster, component); a lane walks ITS cluster's bits in ascending order -- the reference's row
+//           order (kmeans.rs:185-189) -- and adds x[row][component] from shared memory into a register that lives
+//           across tiles.  No sort, no global lists, no gathers.
+// Sums are bit-identical to the other ordered paths (same sequential f32 chain per (cluster, component)).
+// MEASURED (C3, one B200): 4.4 ms per iteration against 1.8 ms for sort + chains -- 20 warp-instructions per (row,
+// subquantizer) pair, most of them the bit-walking loops' branches and index arithmetic (ncu: IMAD 21 %, BRA 10 %,
+// ISETP 10 %, BSYNC / BSSY 12 %; FADD 2 %), half of the shared-memory wavefronts bank conflicts.  Opt-in only
+// (rb_set_kmeans_update(3)); what it would need is the expansion of the bitmaps into per-cluster row lists by ONE lane
+// per cluster, so that the eight component lanes of a cluster do not all walk the bits.
+namespace {
+
+constexpr int kStreamRows = 1024;    // rows per tile (32 bitmap words per cluster: one summary word)
+constexpr int kStreamThreads = 512;  // 16 warps
+
+__global__ void __launch_bounds__(256)
+slab_kernel(const float *__restrict__ x, long long n, long long ldx, int M, int dsub, long long n_pad, float *__restrict__ slabs)
+{
+    // one block: 64 rows x all columns, staged through registers; reads are row-contiguous, writes per-slab contiguous
+    const long long r0 = (long long)blockIdx.x * 64;
+    const int d = M * dsub;
+    for (int e = threadIdx.x; e < 64 * d; e += 256) {
+        const int r = e / d, c = e - r * d;
+        const long long row = r0 + r;
+        if (row < n) {
+            const int m = c / dsub, t = c - m * dsub;
+            slabs[((long long)m * n_pad + row) * dsub + t] = __ldg(x + row * ldx + c);
+        }
+    }
+}
+
+template <int DSUB>
+__global__ void __launch_bounds__(kStreamThreads)
+ordered_stream_kernel(const float *__restrict__ slabs, long long n, long long n_pad, const uint8_t *__restrict__ codes,
+                      long long code_pitch, int M, int k, int KC, float *__restrict__ packed)
+{
+    using namespace ptx;
+    constexpr int CH = 32 / DSUB;  // clusters a warp advances at the same time
+    constexpr int R = kStreamRows;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *sx = reinterpret_cast<float *>(smem);                               // [2][R][DSUB]
+    uint8_t *sc = smem + (size_t)2 * R * DSUB * 4;                             // [2][R]
+    uint32_t *bm = reinterpret_cast<uint32_t *>(sc + 2 * R);                   // [KC][32]
+    uint32_t *sm = bm + (size_t)KC * 32;                                       // [KC] summary words
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + ((KC + 1) & ~1));       // [2]
+    const int m = blockIdx.y, c0 = blockIdx.x * KC;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kc_cur = min(KC, k - c0);
+    const float *slab = slabs + (size_t)m * n_pad * DSUB;
+    const uint8_t *col = codes + (size_t)m * code_pitch;
+    const long long n_tiles = (n + R - 1) / R;
+
+    for (int i = threadIdx.x; i < KC * 32; i += kStreamThreads) bm[i] = 0u;
+    for (int i = threadIdx.x; i < KC; i += kStreamThreads) sm[i] = 0u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto load_tile = [&](long long tile) {  // one thread: the tile's rows of x and their codes, contiguous in memory
+        const int buf = (int)(tile & 1);
+        const long long r0 = tile * R;
+        const long long rows = min((long long)R, n_pad - r0);  // padded rows are readable (slab / code pitch padding)
+        const uint32_t xb = (uint32_t)(rows * DSUB * 4), cb = (uint32_t)((rows + 15) / 16 * 16);
+        mbar_arrive_expect_tx(&bars[buf], xb + cb);
+        bulk_g2s(sx + (size_t)buf * R * DSUB, slab + r0 * DSUB, xb, &bars[buf]);
+        bulk_g2s(sc + (size_t)buf * R, col + r0, cb, &bars[buf]);
+    };
+    if (threadIdx.x == 0 && n_tiles > 0) load_tile(0);
+
+    // chain ownership: warp w advances the clusters w * per_warp + g * CH + cs (g = pass), lane = (cs, t)
+    const int per_warp = (KC + 15) / 16;
+    const int passes = (per_warp + CH - 1) / CH;
+    const int cs = lane / DSUB, t = lane % DSUB;
+    const bool lane_on = cs < CH;
+    constexpr int kMaxPasses = 4;  // KC <= 256: per_warp <= 16, CH >= 1 ... covered by the host's choice of KC
+    float acc[kMaxPasses * 4];
+    unsigned cnt[kMaxPasses * 4];
+#pragma unroll
+    for (int g = 0; g < kMaxPasses * 4; g++) {
+        acc[g] = 0.f;
+        cnt[g] = 0u;
+    }
+
+    for (long long tile = 0; tile < n_tiles; tile++) {
+        const int buf = (int)(tile & 1);
+        // the other buffer was consumed in the previous iteration (barrier at its end): refill it now
+        if (threadIdx.x == 0 && tile + 1 < n_tiles) load_tile(tile + 1);
+        mbar_wait(&bars[buf], (uint32_t)((tile >> 1) & 1));
+        const long long r0 = tile * R;
+        const int rows = (int)min((long long)R, n - r0);
+        const uint8_t *tc = sc + (size_t)buf * R;
+        // ---- route ----
+        for (int r = threadIdx.x; r < rows; r += kStreamThreads) {
+            const int cl = (int)tc[r] - c0;
+            if ((unsigned)cl < (unsigned)kc_cur) {
+                atomicOr(&bm[cl * 32 + (r >> 5)], 1u << (r & 31));
+                atomicOr(&sm[cl], 1u << (r >> 5));
+            }
+        }
+        __syncthreads();
+        // ---- chains ----
+        const float *tx = sx + (size_t)buf * R * DSUB;
+#pragma unroll
+        for (int g = 0; g < kMaxPasses * 4; g++) {
+            if (g >= passes) break;
+            const int cl = warp * per_warp + g * CH + cs;
+            const bool on = lane_on && (g * CH + cs) < per_warp && cl < kc_cur;
+            uint32_t words = on ? sm[cl] : 0u;
+            float a = acc[g];
+            unsigned c = cnt[g];
+            while (__any_sync(0xffffffffu, words != 0u)) {
+                if (words != 0u) {
+                    const int w = __ffs(words) - 1;
+                    words &= words - 1;
+                    uint32_t bits = bm[cl * 32 + w];
+                    c += __popc(bits);
+                    while (bits != 0u) {
+                        const int b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        a = __fadd_rn(a, tx[(size_t)(32 * w + b) * DSUB + t]);  // kmeans.rs:185-189: one rounded add per row
+                    }
+                    if (t == 0) bm[cl * 32 + w] = 0u;
+                }
+            }
+            if (on && t == 0) sm[cl] = 0u;
+            acc[g] = a;
+            cnt[g] = c;
+        }
+        __syncthreads();  // bitmaps are clean and this tile's buffer is free
+    }
+    // results
+    const size_t chains = (size_t)M * k * DSUB;
+#pragma unroll
+    for (int g = 0; g < kMaxPasses * 4; g++) {
+        if (g >= passes) break;
+        const int cl = warp * per_warp + g * CH + cs;
+        if (lane_on && (g * CH + cs) < per_warp && cl < kc_cur) {
+            const size_t mj = (size_t)m * k + c0 + cl;
+            packed[mj * DSUB + t] = acc[g];
+            if (t == 0) packed[chains + mj] = (float)cnt[g];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) packed[chains + (size_t)M * k + m] = 0.f;  // sum ||x||^2: callers keep it in FP64
+}
+
+int stream_cluster_groups(size_t M, size_t k)
+{
+    // as many (subquantizer, cluster group) CTAs as fit twice per SM, at most 8 groups, at least 16 clusters per group
+    int cg = 1;
+    while (cg < 8 && (size_t)(2 * cg) * M <= (size_t)2 * sm_count() && k / (size_t)(2 * cg) >= 16) cg *= 2;
+    return cg;
+}
+
+}  // namespace
+
+bool stream_update_supported(size_t k, size_t dsub)
+{
+    if (k > 256 || k < 16) return false;
+    switch (dsub) {
+    case 2: case 4: case 8: case 16: case 10: case 12: case 6: return true;  // 32 / dsub clusters per warp, tile <= 64 KB
+    default: return false;
+    }
+}
+
+size_t slab_floats(size_t n, size_t d) { return ((n + 15) / 16 * 16 + (size_t)kStreamRows) * d; }
+
+rb_status launch_build_slabs(const float *x, size_t n, ptrdiff_t ldx, size_t M, size_t dsub, float *slabs, cudaStream_t stream)
+{
+    if (n == 0) return RB_OK;
+    const size_t n_pad = (n + 15) / 16 * 16;
+    RB_CUDA_TRY(cudaMemsetAsync(slabs, 0, slab_floats(n, M * dsub) * sizeof(float), stream));
+    slab_kernel<<<(unsigned)ceil_div(n, (size_t)64), 256, 0, stream>>>(x, (long long)n, (long long)ldx, (int)M, (int)dsub,
+                                                                        (long long)n_pad, slabs);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+}
+
+rb_status launch_ordered_stream(const float *slabs, size_t n, const uint8_t *codes, size_t code_pitch, size_t M, size_t k,
+                                size_t dsub, float *packed, cudaStream_t stream)
+{
+    const size_t len = rb_kmeans_packed_len(M, k, dsub);
+    RB_CUDA_TRY(cudaMemsetAsync(packed, 0, len * sizeof(float), stream));
+    if (n == 0) return RB_OK;
+    const int cg = stream_cluster_groups(M, k);
+    const int KC = (int)ceil_div(k, (size_t)cg);
+    const size_t n_pad = (n + 15) / 16 * 16;
+    const size_t smem = (size_t)2 * kStreamRows * dsub * 4 + 2 * kStreamRows + (size_t)KC * 32 * 4 + (size_t)((KC + 1) & ~1) * 4 + 16;
+#define RB_STREAM(D)                                                                                                   \
+    case D: {                                                                                                          \
+        auto kern = ordered_stream_kernel<D>;                                                                          \
+        RB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+        kern<<<dim3((unsigned)cg, (unsigned)M), kStreamThreads, smem, stream>>>(slabs, (long long)n, (long long)n_pad, codes, \
+                                                                                (long long)code_pitch, (int)M, (int)k, KC, packed); \
+        break;                                                                                                         \
+    }
+    switch (dsub) {
+        RB_STREAM(2) RB_STREAM(4) RB_STREAM(6) RB_STREAM(8) RB_STREAM(10) RB_STREAM(12) RB_STREAM(16)
+    default:
+        set_error("streaming update: subvector width %zu is not instantiated", dsub);
+        return RB_ERR_UNSUPPORTED;
+    }
+#undef RB_STREAM
     RB_LAUNCH_CHECK();
     return RB_OK;
 }

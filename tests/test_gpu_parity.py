@@ -651,3 +651,18 @@ def test_opq_train_iteration_matches_the_oracle(oracle, torch_cuda, n, M, k, dsu
     assert np.abs(got_xty - want_xty).max() <= 1e-5 * np.abs(want_xty).max()
     u, _, vt = np.linalg.svd(got_xty, full_matrices=True)
     assert np.abs(u @ vt - want_r).max() <= 1e-4
+
+
+def test_streaming_update_gives_the_same_bits(oracle):
+    """rb_set_kmeans_update(3): the training loop streams subquantizer-major slabs (kmeans.cu ordered_stream_kernel);
+    the sums are the same sequential f32 chains, so the trained codebook is bit-identical (uneven tile, small k)."""
+    x = normal((7_013, 48), 91)
+    for M, bits in ((6, 8), (4, 5)):
+        init = rows_as_initial_centroids(x, M, 1 << bits, 92)
+        want, _ = oracle.train_pq(x, M, bits, 4, 1, init, n_threads=4)
+        rb.set_kmeans_update(3)
+        try:
+            got = rb.Pq.train_pq_using(M, bits, 4, 1, x, None, initial_centroids=init).subquantizers()
+        finally:
+            rb.set_kmeans_update(1)
+        assert np.array_equal(got.view(np.int32), want.view(np.int32))
