@@ -97,11 +97,28 @@ _ERR_CLASSES = {c.status: c for c in (IncorrectNAttempts, IncorrectNIterations, 
                                       IncorrectNumberSubquantizers, NSubquantizersOutsideRange, ConstructRng)}
 
 
+def _point_at_bundled_nccl() -> None:
+    """The library resolves NCCL with dlopen when a communicator spans several devices.  This interpreter's torch
+    carries its own libnccl.so.2 (nvidia/nccl/lib) and the dynamic loader keeps whichever copy of that soname was
+    loaded first, so both must use the same file: name it in RB_NCCL_LIB unless the caller already chose one."""
+    if os.environ.get("RB_NCCL_LIB"):
+        return
+    import importlib.util
+
+    spec = importlib.util.find_spec("nvidia")
+    for root in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(root, "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["RB_NCCL_LIB"] = cand
+            return
+
+
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build the CUDA library first "
             "(python -c 'import __graft_entry__ as g; g.build()').  reductive_b200 has no CPU fallback.")
+    _point_at_bundled_nccl()
     lib = C.CDLL(LIB_PATH)
     sz, pd, vp, fp = C.c_size_t, C.c_ssize_t, C.c_void_p, C.c_void_p
     lib.rb_last_error_message.restype = C.c_char_p

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) assemble_codes_kernel(const __grid_consta
     }
 }
 
-// NCCL is resolved at run time (libnccl.so.2): a process that already carries one (torch) keeps using that copy.
+// NCCL is resolved at run time (dlopen), only when a communicator over more than one device is asked for.
 struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
@@ -72,8 +72,15 @@ const NcclApi &nccl()
 {
     static NcclApi api = []() {
         NcclApi a;
-        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        // Order: the copy named by RB_NCCL_LIB, the copy the process already carries, the system one.  A host that
+        // will load another NCCL later under the same soname (torch's bundled libnccl.so.2) must point RB_NCCL_LIB
+        // at that file: the dynamic loader keeps whichever libnccl.so.2 came first for everyone.
+        void *h = nullptr;
+        if (const char *path = getenv("RB_NCCL_LIB"))
+            if (*path) h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
         if (!h) return a;
 #define RB_SYM(name) a.name = reinterpret_cast<decltype(a.name)>(dlsym(h, "nccl" #name))
         RB_SYM(GetUniqueId); RB_SYM(CommInitRank); RB_SYM(CommInitAll); RB_SYM(CommDestroy); RB_SYM(GroupStart);

@@ -169,3 +169,20 @@ def test_f64_entry_points_answer_unsupported():
     lib.rb_pq_create_f64.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]
     assert lib.rb_pq_create_f64(q.ctypes.data, 1, 2, 2, None, C.byref(h)) == ERR_UNSUPPORTED
     assert "f32 only" in last_error() and not h.value
+
+
+def test_nccl_is_resolved_to_the_copy_torch_uses():
+    """The library dlopens NCCL lazily; if that happened before `import torch` with another libnccl.so.2 than the one
+    torch is linked against, the later torch import would fail on a missing symbol.  Fresh interpreter: resolve NCCL
+    through the library first, then import torch."""
+    import subprocess
+    import sys
+
+    code = ("import ctypes, reductive_b200._cabi as c\n"
+            "buf = (ctypes.c_ubyte * 128)()\n"
+            "assert c.lib.rb_comm_unique_id(buf, 128) == 0, c.last_error()\n"
+            "import torch\n"
+            "print('ok', torch.__version__)\n")
+    env = {k: v for k, v in os.environ.items() if k != "RB_NCCL_LIB"}
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
