@@ -376,6 +376,10 @@ sort_local_kernel(const uint8_t *__restrict__ codes, long long code_pitch, long 
 
 // read-only load that asks L2 to bring in the whole 128-byte line: the line's other three 32-byte pieces belong to
 // neighbouring subquantizers of the same row and are gathered by other warps during the same launch
+// programmatic dependent launch: wait for the previous launch of the stream / let the next one start early
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float ldg_l2_128(const float *p)
 {
     float v;
@@ -402,10 +406,12 @@ ordered_chain_kernel(const float *__restrict__ x, long long ldx, int M, int k, i
     const long long chains = total_mj * DSUB;
     const long long mjc = on ? mj : 0;
     const int m = (int)(mjc / k), j = (int)(mjc % k);
-    // the chain so far: other ranks' rows (init) before this rank's first chunk, else what the last launch left
-    const float *prev = chunk == 0 ? init : packed;
-    float acc = (on && prev) ? prev[mjc * DSUB + t] : 0.f;
-    double sq = 0.0;
+    // Launched with programmatic stream serialization after the first chunk: everything up to griddep_wait() runs
+    // while the previous chunk's launch is still draining -- the cluster boundaries, the first row offsets and the
+    // first batch of gathers depend only on the sort and on x, which were complete before the first chain launch
+    // passed its own wait.  Only the running sums (prev) need the previous launch.
+    if (chunk == 0) griddep_wait();
+    griddep_launch_dependents();
     unsigned s = 0, e = 0;
     if (on) {
         const uint32_t *ls = lstart + ((size_t)chunk * M + m) * (k + 1) + j;
@@ -424,24 +430,28 @@ ordered_chain_kernel(const float *__restrict__ x, long long ldx, int M, int k, i
     // the adds are predicated.  The row offsets of batch b + 1 are fetched while batch b's gathers are in flight, so a
     // batch costs one memory round trip, not two.
     unsigned off[UN];
-    {
-        const uint16_t *spu = rem > 0 ? sp : seg0;
-        const int last = max(min(rem, UN), 1) - 1;
+    float v[UN];
+    auto fetch_offsets = [&](int left) {  // offsets of the batch that starts at sp with `left` rows still to add
+        const uint16_t *spu = left > 0 ? sp : seg0;
+        const int last = max(min(left, UN), 1) - 1;
 #pragma unroll
         for (int u = 0; u < UN; u++) off[u] = (unsigned)__ldg(spu + min(u, last));
-    }
-    while (__any_sync(0xffffffffu, rem > 0)) {
-        float v[UN];
+    };
+    auto gather = [&]() {
 #pragma unroll
         for (int u = 0; u < UN; u++) v[u] = ldg_l2_128(reinterpret_cast<const float *>(xc + (unsigned long long)off[u] * (unsigned long long)pitch_b));
-        sp += UN;
-        const int rem_next = rem - UN;
-        {
-            const uint16_t *spu = rem_next > 0 ? sp : seg0;
-            const int last = max(min(rem_next, UN), 1) - 1;
-#pragma unroll
-            for (int u = 0; u < UN; u++) off[u] = (unsigned)__ldg(spu + min(u, last));
-        }
+    };
+    fetch_offsets(rem);
+    gather();
+    sp += UN;
+    int rem_next = rem - UN;
+    fetch_offsets(rem_next);
+    if (chunk != 0) griddep_wait();
+    // the chain so far: other ranks' rows (init) before this rank's first chunk, else what the last launch left
+    const float *prev = chunk == 0 ? init : packed;
+    float acc = (on && prev) ? prev[mjc * DSUB + t] : 0.f;
+    double sq = 0.0;
+    while (__any_sync(0xffffffffu, rem > 0)) {
 #pragma unroll
         for (int u = 0; u < UN; u++) {
             if (u < rem) {
@@ -450,6 +460,10 @@ ordered_chain_kernel(const float *__restrict__ x, long long ldx, int M, int k, i
             }
         }
         rem = rem_next;
+        gather();
+        sp += UN;
+        rem_next = rem - UN;
+        fetch_offsets(rem_next);
     }
     sq = (double)sqf;
     if (on) {
@@ -497,21 +511,35 @@ rb_status launch_ordered_fast(const float *x, size_t n, ptrdiff_t ldx, const uin
         }
         const unsigned blocks = (unsigned)ceil_div(ceil_div(M * k, 32 / dsub), 8);
         const bool deep = M * k * dsub <= (size_t)sm_count() * 512;  // fewer than ~16 chain warps per SM
+        // chunk 0 is an ordinary launch (it needs the sort); the others may start while their predecessor drains
+        cudaLaunchAttribute pdl[1];
+        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl[0].val.programmaticStreamSerializationAllowed = 1;
         for (size_t c = 0; c < n_chunks; c++) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(blocks);
+            cfg.blockDim = dim3(256);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = stream;
+            cfg.attrs = pdl;
+            cfg.numAttrs = c > 0 ? 1 : 0;
 #define RB_CHAIN(D)                                                                                                  \
     case D:                                                                                                          \
         if (deep)                                                                                                    \
-            ordered_chain_kernel<D, 32><<<blocks, 256, 0, stream>>>(x, (long long)ldx, (int)M, (int)k, (int)n_chunks, \
-                                                                    (int)c, kChunkRows, list, lstart, init, packed);  \
+            RB_CUDA_TRY(cudaLaunchKernelEx(&cfg, ordered_chain_kernel<D, 32>, x, (long long)ldx, (int)M, (int)k,     \
+                                           (int)n_chunks, (int)c, kChunkRows, (const uint16_t *)list,                \
+                                           (const uint32_t *)lstart, init, packed));                                 \
         else                                                                                                         \
-            ordered_chain_kernel<D, 8><<<blocks, 256, 0, stream>>>(x, (long long)ldx, (int)M, (int)k, (int)n_chunks,  \
-                                                                   (int)c, kChunkRows, list, lstart, init, packed);   \
+            RB_CUDA_TRY(cudaLaunchKernelEx(&cfg, ordered_chain_kernel<D, 8>, x, (long long)ldx, (int)M, (int)k,      \
+                                           (int)n_chunks, (int)c, kChunkRows, (const uint16_t *)list,                \
+                                           (const uint32_t *)lstart, init, packed));                                 \
         break;
             switch (dsub) {
                 RB_CHAIN(1) RB_CHAIN(2) RB_CHAIN(3) RB_CHAIN(4) RB_CHAIN(5) RB_CHAIN(6) RB_CHAIN(8) RB_CHAIN(10)
                 RB_CHAIN(12) RB_CHAIN(15) RB_CHAIN(16) RB_CHAIN(20) RB_CHAIN(30) RB_CHAIN(32)
             default: break;
             }
+#undef RB_CHAIN
             RB_LAUNCH_CHECK();
         }
         return RB_OK;
