@@ -323,7 +323,7 @@ def run_ours(args) -> None:
     loss3 = torch.zeros((M3,), device=dev)
     log("k-means: initial centroids ready")
     # the training-loop state of the library (csrc/dist.cu; a single rank exchanges nothing): both layouts of the rows,
-    # FP64 sum of squares, streaming ordered update
+    # FP64 sum of squares, ordered update
     comm = Comm() if world > 1 else Comm(rank=0, world=1)
     km = ShardedKMeans(comm, x3, M3, K_CENTROIDS, dsub3)
     step3 = lambda c, l=None: km.iterate(c, l)  # noqa: E731
@@ -376,7 +376,7 @@ def run_ours(args) -> None:
                     f"rows sharded over {world} GPU(s)",
         "sec_per_iter": it_ms * 1e-3, "iters_timed": iters3,
         "mode": "sharded: assignment by rows, ordered update by subquantizers (NCCL inside the C++ library)" if world > 1
-                else "one GPU: assignment + streaming ordered update (reference summation order)",
+                else "one GPU: tensor-core assignment + ordered update (chunk sort + one sequential chain per cluster: the reference's summation order)",
         "bit_identical_to_1gpu": bit_identical,
         "bit_identity_checked_against": "a one-GPU run of the same rows through rb_kmeans_assign_accumulate / rb_kmeans_finalize "
                                         "(sort + chain kernels)",
