@@ -237,6 +237,36 @@ rb_status rb_opq_train_iteration(const float *x, size_t n, size_t d, ptrdiff_t x
                                  float *centroids, size_t n_subquantizers, size_t n_centroids, float *xty_out,
                                  void *stream);
 
+/* ---- caller-side quantized storage ----------------------------------------------------
+ * finalfusion keeps a trained Pq<f32> as a "quantized array": the quantizer, the [n, M] u8 codes produced by
+ * QuantizeVector::quantize_batch (traits.rs:77-87) and optionally one norm per row (rows are l2-normalised before
+ * quantisation); its lookup is  embedding(i) = Reconstruct::reconstruct(codes[i]) * norm[i]  (traits.rs:102-156,
+ * pq.rs:303-347).  That type is outside /root/reference; these entry points are what a binding of it would call.
+ * The store keeps codes and norms resident in HBM and BORROWS the quantizer (destroy the store first).
+ * u8 codes only: a quantizer with more than 256 centroids answers RB_ERR_CODE_TYPE. */
+typedef struct rb_qstore rb_qstore;
+/* codes: [n, M] u8 with row stride code_row_stride (elements, unit column stride); norms_or_null: [n] f32; both in
+ * mem_kind memory.  Copies them; a code >= n_centroids answers RB_ERR_CODE_RANGE.  Synchronises `stream`. */
+rb_status rb_qstore_create(const rb_pq *pq, const uint8_t *codes, size_t n, ptrdiff_t code_row_stride,
+                           const float *norms_or_null, int mem_kind, void *stream, rb_qstore **out);
+void rb_qstore_destroy(rb_qstore *store);
+size_t rb_qstore_len(const rb_qstore *store);
+int rb_qstore_has_norms(const rb_qstore *store);
+/* out[i, :] = reconstruct(codes[indices[i]]) (projection applied as in pq.rs:323-326) * norms[indices[i]]:
+ * bit-exact without a projection, within 1e-5 with one (as rb_pq_reconstruct_batch).  indices: [n_idx] u64 and out:
+ * [n_idx, d] with element strides, both in mem_kind memory.  An index >= len answers RB_ERR_INVALID (the reference
+ * panics on the out-of-bounds row).  Synchronises `stream`. */
+rb_status rb_qstore_embeddings(const rb_qstore *store, const uint64_t *indices, size_t n_idx, float *out,
+                               ptrdiff_t out_row_stride, ptrdiff_t out_col_stride, int mem_kind, void *stream);
+/* Fused decode + dot: out[q, i] = queries[q, :] . embedding(i) for every stored row, without materialising the
+ * [n, d] reconstruction: per query one table of subvector-centroid dot products (the query is rotated by the
+ * projection first, q . (y R^T) = (q R) . y), then one pass over the codes per batch of up to 8 queries.  f32
+ * accumulation, subquantizers in ascending order: within 1e-5 * sum_c |q_c| |e_c| of the exact product.
+ * queries: [nq, d] with element strides; out: [nq, len] with row stride out_row_stride; both in mem_kind memory.
+ * DEVICE calls are asynchronous on `stream`. */
+rb_status rb_qstore_dot(const rb_qstore *store, const float *queries, size_t nq, ptrdiff_t query_row_stride,
+                        ptrdiff_t query_col_stride, float *out, ptrdiff_t out_row_stride, int mem_kind, void *stream);
+
 /* ---- A = f64 --------------------------------------------------------------------------------------- */
 
 /* Pq<A> is generic over NdFloat (pq.rs:29-32,196-203; linalg.rs:150-156); every configuration this library was built

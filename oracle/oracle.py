@@ -299,6 +299,24 @@ class Oracle:
         u, _, vt = np.linalg.svd(xty, full_matrices=True)
         return self.sgemm(np.ascontiguousarray(u, np.float32), np.ascontiguousarray(vt, np.float32)), c, xty
 
+    # ---- caller-side quantized storage.  PARITY UNPINNED: the storage type lives in the finalfusion
+    # crate, outside /root/reference, so no reference-held vector exists for it; these restate its documented behaviour
+    # (embedding = Reconstruct::reconstruct (traits.rs:102-156, pq.rs:303-347) times the stored norm) on top of the
+    # pinned reconstruct_batch above.
+    def qstore_embeddings(self, quantizers, projection, codes, norms, indices):
+        idx = np.asarray(indices, np.int64)
+        e = self.reconstruct_batch(quantizers, projection, np.ascontiguousarray(np.asarray(codes)[idx]))
+        if norms is not None:
+            e = e * np.asarray(norms, np.float32)[idx][:, None]  # f32 `*=`, one rounded multiply per element
+        return e.astype(np.float32)
+
+    def qstore_dot(self, quantizers, projection, codes, norms, queries):
+        """Exact (float64) scores of every row against every query and the magnitude sum_c |q_c| |e_c| the f32
+        tolerance of the fused kernel is stated against."""
+        e = self.qstore_embeddings(quantizers, projection, codes, norms, np.arange(len(codes))).astype(np.float64)
+        q = np.asarray(queries, np.float64)
+        return q @ e.T, np.abs(q) @ np.abs(e).T
+
 
 _default = None
 

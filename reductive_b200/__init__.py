@@ -15,8 +15,10 @@ from .kmeans import (  # noqa: F401
 )
 from .opq import GaussianOpq, Opq, bucket_eigenvalues  # noqa: F401
 from .pq import Pq, QuantizeVector, Reconstruct, TrainPq, check_quantizer_invariants  # noqa: F401
+from .storage import QuantizedArray  # noqa: F401
 
 __all__ = [
     "Pq", "Opq", "GaussianOpq", "TrainPq", "QuantizeVector", "Reconstruct", "KMeans", "NIterationsCondition",
     "RandomInstanceCentroids", "kmeans_iteration", "kmeans_with_centroids", "ReductiveError", "ReductivePanic",
+    "QuantizedArray",
 ]

@@ -48,6 +48,7 @@ EXPORTED_SYMBOLS = [
     "rb_dist_subquantizer_range", "rb_comm_unique_id", "rb_comm_create", "rb_comm_destroy", "rb_comm_rank",
     "rb_comm_world", "rb_kmeans_dist_create", "rb_kmeans_dist_iterate", "rb_kmeans_dist_destroy", "rb_pq_train_dist",
     "rb_pq_train_multi", "rb_covariance", "rb_opq_train_iteration", "rb_pq_create_f64", "rb_pq_quantize_batch_f64", "rb_pq_reconstruct_batch_f64", "rb_pq_train_f64",
+    "rb_qstore_create", "rb_qstore_destroy", "rb_qstore_len", "rb_qstore_has_norms", "rb_qstore_embeddings", "rb_qstore_dot",
 ]
 
 
@@ -133,6 +134,14 @@ def _load() -> C.CDLL:
     lib.rb_set_host_copy_threads.argtypes = [C.c_int]
     lib.rb_pq_destroy.argtypes = [vp]
     lib.rb_pq_destroy.restype = None
+    lib.rb_qstore_create.argtypes = [vp, vp, sz, pd, fp, C.c_int, vp, C.POINTER(vp)]
+    lib.rb_qstore_destroy.argtypes = [vp]
+    lib.rb_qstore_destroy.restype = None
+    lib.rb_qstore_len.argtypes = [vp]
+    lib.rb_qstore_len.restype = sz
+    lib.rb_qstore_has_norms.argtypes = [vp]
+    lib.rb_qstore_embeddings.argtypes = [vp, vp, sz, fp, pd, pd, C.c_int, vp]
+    lib.rb_qstore_dot.argtypes = [vp, fp, sz, pd, pd, fp, pd, C.c_int, vp]
     for name in ("rb_pq_quantized_len", "rb_pq_reconstructed_len", "rb_pq_n_quantizer_centroids"):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = sz

@@ -1202,4 +1202,199 @@ rb_status rb_project_rows(const float *x, size_t n, size_t d, ptrdiff_t rs, ptrd
     return launch_project(x, n, d, rs, cs, r_dev, transpose_r, out, (cudaStream_t)stream);
 }
 
+// ---- caller-side quantized storage (kernels in qstore.cu) ------------------------------------------
+struct rb_qstore {
+    const rb_pq *pq = nullptr;  // borrowed
+    size_t n = 0;
+    uint8_t *codes = nullptr;  // DEVICE [n][M], allocation padded to 16 bytes
+    float *norms = nullptr;    // DEVICE [n] or null
+};
+
+namespace {
+struct DeviceScope {  // make the quantizer's device current for a host-memory call
+    int prev = 0;
+    bool switched = false;
+    rb_status enter(int device)
+    {
+        RB_CUDA_TRY(cudaGetDevice(&prev));
+        if (prev != device) {
+            RB_CUDA_TRY(cudaSetDevice(device));
+            switched = true;
+        }
+        return RB_OK;
+    }
+    ~DeviceScope()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+}  // namespace
+
+void rb_qstore_destroy(rb_qstore *s)
+{
+    if (!s) return;
+    DeviceScope scope;
+    if (s->pq) scope.enter(s->pq->device);
+    cudaFree(s->codes);
+    cudaFree(s->norms);
+    delete s;
+}
+
+rb_status rb_qstore_create(const rb_pq *pq, const uint8_t *codes, size_t n, ptrdiff_t code_row_stride,
+                           const float *norms_or_null, int mem_kind, void *stream, rb_qstore **out)
+{
+    if (!out) return fail(RB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!pq || (n && !codes)) return fail(RB_ERR_INVALID, "NULL argument");
+    if (mem_kind != RB_MEM_HOST && mem_kind != RB_MEM_DEVICE) return fail(RB_ERR_INVALID, "bad mem_kind");
+    if (pq->k > 256) return fail(RB_ERR_CODE_TYPE, "Cannot store centroids in quantizer index type");  // u8 codes
+    if (code_row_stride < (ptrdiff_t)pq->M) return fail(RB_ERR_SHAPE, "code rows overlap (stride %td < %zu)", code_row_stride, pq->M);
+    RB_TRY(require_device());
+    DeviceScope scope;
+    if (mem_kind == RB_MEM_HOST) RB_TRY(scope.enter(pq->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    rb_qstore *s = new rb_qstore();
+    s->pq = pq;
+    s->n = n;
+    auto body = [&]() -> rb_status {
+        const size_t M = pq->M, bytes = (n * M + 15) & ~(size_t)15;
+        RB_CUDA_TRY(cudaMalloc((void **)&s->codes, bytes ? bytes : 16));
+        RB_CUDA_TRY(cudaMemsetAsync(s->codes, 0, bytes ? bytes : 16, st));
+        const cudaMemcpyKind kind = mem_kind == RB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        if (n) RB_CUDA_TRY(cudaMemcpy2DAsync(s->codes, M, codes, (size_t)code_row_stride, M, n, kind, st));
+        if (norms_or_null) {
+            RB_CUDA_TRY(cudaMalloc((void **)&s->norms, (n ? n : 1) * sizeof(float)));
+            if (n) RB_CUDA_TRY(cudaMemcpyAsync(s->norms, norms_or_null, n * sizeof(float), kind, st));
+        }
+        // every stored code must name a centroid (quantize_batch guarantees it; reconstruct would panic otherwise)
+        Workspace flag;
+        RB_TRY(flag.alloc(sizeof(int), st));
+        RB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+        RB_TRY(launch_qstore_check_codes(s->codes, n * M, pq->k, flag.as<int>(), st));
+        int bad = 0;
+        RB_CUDA_TRY(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RB_CUDA_TRY(cudaStreamSynchronize(st));
+        if (bad) return fail(RB_ERR_CODE_RANGE, "a code is >= the number of centroids (%zu)", pq->k);
+        return RB_OK;
+    };
+    const rb_status r = body();
+    if (r != RB_OK) {
+        rb_qstore_destroy(s);
+        return r;
+    }
+    *out = s;
+    return RB_OK;
+}
+
+size_t rb_qstore_len(const rb_qstore *s) { return s ? s->n : 0; }
+int rb_qstore_has_norms(const rb_qstore *s) { return s && s->norms ? 1 : 0; }
+
+rb_status rb_qstore_embeddings(const rb_qstore *s, const uint64_t *indices, size_t n_idx, float *out, ptrdiff_t ors,
+                               ptrdiff_t ocs, int mem_kind, void *stream)
+{
+    if (!s) return fail(RB_ERR_INVALID, "store is NULL");
+    if (mem_kind != RB_MEM_HOST && mem_kind != RB_MEM_DEVICE) return fail(RB_ERR_INVALID, "bad mem_kind");
+    if (n_idx == 0) return RB_OK;
+    if (!indices || !out) return fail(RB_ERR_INVALID, "NULL data pointer");
+    RB_TRY(require_device());
+    const rb_pq *pq = s->pq;
+    const size_t M = pq->M, d = pq->d;
+    DeviceScope scope;
+    if (mem_kind == RB_MEM_HOST) RB_TRY(scope.enter(pq->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace idx_dev, sel, nsel, flag, dense;
+    const unsigned long long *idx = reinterpret_cast<const unsigned long long *>(indices);
+    if (mem_kind == RB_MEM_HOST) {
+        RB_TRY(idx_dev.alloc(n_idx * sizeof(uint64_t), st));
+        RB_CUDA_TRY(cudaMemcpyAsync(idx_dev.p, indices, n_idx * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        idx = idx_dev.as<unsigned long long>();
+    }
+    RB_TRY(sel.alloc(n_idx * M + 16, st));
+    if (s->norms) RB_TRY(nsel.alloc(n_idx * sizeof(float), st));
+    RB_TRY(flag.alloc(2 * sizeof(int), st));
+    RB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
+    RB_TRY(launch_qstore_select(s->codes, s->n, M, idx, n_idx, sel.as<uint8_t>(), s->norms, s->norms ? nsel.as<float>() : nullptr,
+                                flag.as<int>(), st));
+    float *dst = out;
+    ptrdiff_t drs = ors, dcs = ocs;
+    if (mem_kind == RB_MEM_HOST) {
+        RB_TRY(dense.alloc(n_idx * d * sizeof(float), st));
+        dst = dense.as<float>();
+        drs = (ptrdiff_t)d;
+        dcs = 1;
+    }
+    // reconstruct (pq.rs:303-347, projection included), then scale by the row's norm
+    RB_TRY(reconstruct_batch_device(pq, sel.p, 1, n_idx, (ptrdiff_t)M, 1, dst, drs, dcs, flag.as<int>() + 1, st));
+    if (s->norms) RB_TRY(launch_qstore_scale_rows(dst, drs, dcs, n_idx, d, nsel.as<float>(), st));
+    int bad = 0;
+    RB_CUDA_TRY(cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (mem_kind == RB_MEM_HOST) {
+        if (ocs == 1)
+            RB_CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)ors * sizeof(float), dst, d * sizeof(float), d * sizeof(float), n_idx,
+                                          cudaMemcpyDeviceToHost, st));
+        else {
+            std::vector<float> tmp(n_idx * d);
+            RB_CUDA_TRY(cudaMemcpyAsync(tmp.data(), dst, n_idx * d * sizeof(float), cudaMemcpyDeviceToHost, st));
+            RB_CUDA_TRY(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < n_idx; i++)
+                for (size_t c = 0; c < d; c++) out[(ptrdiff_t)i * ors + (ptrdiff_t)c * ocs] = tmp[i * d + c];
+        }
+    }
+    RB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (bad) return fail(RB_ERR_INVALID, "an index is >= the number of stored rows (%zu)", s->n);
+    return RB_OK;
+}
+
+rb_status rb_qstore_dot(const rb_qstore *s, const float *queries, size_t nq, ptrdiff_t qrs, ptrdiff_t qcs, float *out,
+                        ptrdiff_t out_row_stride, int mem_kind, void *stream)
+{
+    if (!s) return fail(RB_ERR_INVALID, "store is NULL");
+    if (mem_kind != RB_MEM_HOST && mem_kind != RB_MEM_DEVICE) return fail(RB_ERR_INVALID, "bad mem_kind");
+    if (nq == 0 || s->n == 0) return RB_OK;
+    if (!queries || !out) return fail(RB_ERR_INVALID, "NULL data pointer");
+    if (out_row_stride < (ptrdiff_t)s->n) return fail(RB_ERR_SHAPE, "score rows overlap (stride %td < %zu)", out_row_stride, s->n);
+    RB_TRY(require_device());
+    const rb_pq *pq = s->pq;
+    const size_t M = pq->M, d = pq->d, k = pq->k, n = s->n;
+    DeviceScope scope;
+    if (mem_kind == RB_MEM_HOST) RB_TRY(scope.enter(pq->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace qd, qrot, lut, scores;
+    const float *q = queries;
+    ptrdiff_t rs = qrs, cs = qcs;
+    if (mem_kind == RB_MEM_HOST) {
+        std::vector<float> packed(nq * d);
+        for (size_t i = 0; i < nq; i++)
+            for (size_t c = 0; c < d; c++) packed[i * d + c] = queries[(ptrdiff_t)i * qrs + (ptrdiff_t)c * qcs];
+        RB_TRY(qd.alloc(nq * d * sizeof(float), st));
+        RB_CUDA_TRY(cudaMemcpyAsync(qd.p, packed.data(), nq * d * sizeof(float), cudaMemcpyHostToDevice, st));
+        RB_CUDA_TRY(cudaStreamSynchronize(st));  // `packed` goes away
+        q = qd.as<float>();
+        rs = (ptrdiff_t)d;
+        cs = 1;
+    }
+    // q . (y R^T) = (q R) . y: rotate the query like an encode input (pq.rs:276), or just pack it
+    RB_TRY(qrot.alloc(nq * d * sizeof(float), st));
+    if (pq->proj_dev)
+        RB_TRY(launch_project(q, nq, d, rs, cs, pq->proj_dev, 0, qrot.as<float>(), st));
+    else
+        RB_TRY(launch_pack_rows(q, nq, d, rs, cs, qrot.as<float>(), st));
+    RB_TRY(lut.alloc(qstore_lut_floats(M, k, nq) * sizeof(float), st));
+    float *dst = out;
+    ptrdiff_t dld = out_row_stride;
+    if (mem_kind == RB_MEM_HOST) {
+        RB_TRY(scores.alloc(nq * n * sizeof(float), st));
+        dst = scores.as<float>();
+        dld = (ptrdiff_t)n;
+    }
+    RB_TRY(launch_qstore_dot(s->codes, n, pq->q_dev, M, k, pq->dsub, qrot.as<float>(), nq, s->norms, lut.as<float>(), dst, dld, st));
+    if (mem_kind == RB_MEM_HOST) {
+        RB_CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)out_row_stride * sizeof(float), dst, n * sizeof(float), n * sizeof(float), nq,
+                                      cudaMemcpyDeviceToHost, st));
+        RB_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return RB_OK;
+}
+
 }  // extern "C"
+

@@ -252,6 +252,19 @@ rb_status launch_column_means(const float *x, size_t n, size_t d, ptrdiff_t ldx,
 rb_status launch_gram(const float *a, ptrdiff_t lda, const float *b, ptrdiff_t ldb, size_t n, size_t da, size_t db,
                       const float *a_sub, const float *b_sub, float b_div, float *out, cudaStream_t stream);
 
+// qstore.cu -- caller-side quantized storage: row lookups and the fused decode + dot scan.  codes: dense [n][M] u8,
+// allocation padded to a multiple of 16 bytes.  lut: workspace of qstore_lut_floats(M, k, nq) floats.
+rb_status launch_qstore_select(const uint8_t *codes, size_t n, size_t M, const unsigned long long *idx, size_t n_idx,
+                               uint8_t *out, const float *norms, float *norms_out, int *err, cudaStream_t stream);
+rb_status launch_qstore_scale_rows(float *out, ptrdiff_t ors, ptrdiff_t ocs, size_t n, size_t d, const float *norms_sel,
+                                   cudaStream_t stream);
+rb_status launch_qstore_check_codes(const uint8_t *codes, size_t bytes, size_t k, int *err, cudaStream_t stream);
+int qstore_queries_per_pass(size_t M, size_t k, size_t nq);
+size_t qstore_lut_floats(size_t M, size_t k, size_t nq);
+rb_status launch_qstore_dot(const uint8_t *codes, size_t n, const float *cent, size_t M, size_t k, size_t dsub,
+                            const float *qrot, size_t nq, const float *norms, float *lut, float *out, ptrdiff_t out_ld,
+                            cudaStream_t stream);
+
 // Streaming ordered update for training loops (kmeans.cu): x laid out once as subquantizer-major slabs
 // (slab_floats(n, d) floats), then per iteration one pass that streams the slabs; sums bit-identical to the chain path.
 bool stream_update_supported(size_t k, size_t dsub);
