@@ -323,6 +323,10 @@ rb_status rb_kmeans_dist_create(rb_comm *comm, const float *x_local, size_t n_lo
  * DEVICE [M].  Collective, asynchronous on `stream`. */
 rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *state, float *centroids, float *loss_or_null, void *stream);
 void rb_kmeans_dist_destroy(rb_kmeans_dist *state);
+/* 1: the assignments are stored by the assignment kernels straight into their owners' memory (the [M][pitch] code
+ * matrix is one peer-mapped address range: cuMemCreate / cuMemMap, descriptors passed between the ranks of the node);
+ * 0: they are exchanged with ncclSend/Recv (single rank, no peer access, RB_DIST_P2P=0).  Same result either way. */
+int rb_kmeans_dist_peer_window(const rb_kmeans_dist *state);
 
 /* TrainPq::train_pq_using for Pq (pq.rs:201-249) over rows sharded across the ranks of `comm`; every rank passes
  * its own rows (instances_local: [n_local, d], mem_kind; unit column stride) and the same initial centroids (HOST

@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     "rb_kmeans_accumulate",
     "rb_kmeans_finalize", "rb_pq_train", "rb_project_rows",
     "rb_dist_subquantizer_range", "rb_comm_unique_id", "rb_comm_create", "rb_comm_destroy", "rb_comm_rank",
-    "rb_comm_world", "rb_kmeans_dist_create", "rb_kmeans_dist_iterate", "rb_kmeans_dist_destroy", "rb_pq_train_dist",
+    "rb_comm_world", "rb_kmeans_dist_create", "rb_kmeans_dist_iterate", "rb_kmeans_dist_destroy", "rb_kmeans_dist_peer_window", "rb_pq_train_dist",
     "rb_pq_train_multi", "rb_covariance", "rb_opq_train_iteration", "rb_pq_create_f64", "rb_pq_quantize_batch_f64", "rb_pq_reconstruct_batch_f64", "rb_pq_train_f64",
     "rb_qstore_create", "rb_qstore_destroy", "rb_qstore_len", "rb_qstore_has_norms", "rb_qstore_embeddings", "rb_qstore_dot",
 ]
@@ -177,6 +177,7 @@ def _load() -> C.CDLL:
     lib.rb_kmeans_dist_create.argtypes = [vp, fp, sz, pd, sz, sz, sz, vp, C.POINTER(vp)]
     lib.rb_kmeans_dist_iterate.argtypes = [vp, fp, fp, vp]
     lib.rb_kmeans_dist_destroy.argtypes = [vp]
+    lib.rb_kmeans_dist_peer_window.argtypes = [vp]
     lib.rb_kmeans_dist_destroy.restype = None
     lib.rb_pq_train_dist.argtypes = [vp, fp, sz, sz, sz, pd, sz, C.c_uint32, sz, sz, fp, fp, C.c_int, vp, C.POINTER(vp)]
     lib.rb_pq_train_multi.argtypes = [C.POINTER(C.c_int), C.c_int, fp, sz, sz, pd, sz, C.c_uint32, sz, sz, fp, fp,

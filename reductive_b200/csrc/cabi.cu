@@ -970,10 +970,19 @@ int rb_kmeans_code_width(size_t k) { return k <= 256 ? 1 : 4; }
 rb_status rb_kmeans_assign(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids, size_t M, size_t k,
                            size_t dsub, void *codes, void *stream)
 {
+    return rb::kmeans_assign_strided(x, n_local, ldx, centroids, M, k, dsub, codes, (ptrdiff_t)rb_kmeans_code_pitch(n_local),
+                                     (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// column-major codes with an explicit column stride (elements): dist.cu points it at the peer-mapped code matrix
+rb_status rb::kmeans_assign_strided(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids, size_t M, size_t k,
+                                    size_t dsub, void *codes, ptrdiff_t col_stride, cudaStream_t st)
+{
     if (!centroids || !codes || (n_local && !x)) return fail(RB_ERR_INVALID, "NULL argument");
     if (M == 0 || k == 0 || dsub == 0) return fail(RB_ERR_SHAPE, "Cannot cluster instances with zero centroids.");
     RB_TRY(require_device());
-    cudaStream_t st = (cudaStream_t)stream;
     Workspace cs;
     RB_TRY(cs.alloc(M * k * sizeof(float), st));
     RB_TRY(launch_centroid_norms(centroids, M * k, dsub, cs.as<float>(), st));
@@ -982,11 +991,12 @@ rb_status rb_kmeans_assign(const float *x, size_t n_local, ptrdiff_t ldx, const 
     if (g_encode_algo.load() != RB_ENCODE_EXACT) RB_TRY(tc.prepare(cb, st));
     // column-major [M][pitch]: the tensor kernel's row-per-thread stores and the per-subquantizer sort both touch
     // contiguous bytes
-    const rb_status s = encode_device(cb, &tc, x, n_local, ldx, 0, codes, rb_kmeans_code_width(k), 1,
-                                      (ptrdiff_t)rb_kmeans_code_pitch(n_local), st);  // kmeans.rs:319
+    const rb_status s = encode_device(cb, &tc, x, n_local, ldx, 0, codes, rb_kmeans_code_width(k), 1, col_stride, st);  // kmeans.rs:319
     tc.release_async(st);
     return s;
 }
+
+extern "C" {
 
 rb_status rb_kmeans_accumulate(const float *x, size_t n_local, ptrdiff_t ldx, const void *codes, size_t M, size_t k,
                                size_t dsub, const float *packed_before, float *packed, void *stream)

@@ -252,6 +252,10 @@ rb_status launch_column_means(const float *x, size_t n, size_t d, ptrdiff_t ldx,
 rb_status launch_gram(const float *a, ptrdiff_t lda, const float *b, ptrdiff_t ldb, size_t n, size_t da, size_t db,
                       const float *a_sub, const float *b_sub, float b_div, float *out, cudaStream_t stream);
 
+// cabi.cu -- cluster_assignments of all subquantizers into column-major codes with column stride col_stride (elements)
+rb_status kmeans_assign_strided(const float *x, size_t n_local, ptrdiff_t ldx, const float *centroids, size_t M, size_t k,
+                                size_t dsub, void *codes, ptrdiff_t col_stride, cudaStream_t stream);
+
 // qstore.cu -- caller-side quantized storage: row lookups and the fused decode + dot scan.  codes: dense [n][M] u8,
 // allocation padded to a multiple of 16 bytes.  lut: workspace of qstore_lut_floats(M, k, nq) floats.
 rb_status launch_qstore_select(const uint8_t *codes, size_t n, size_t M, const unsigned long long *idx, size_t n_idx,

@@ -12,12 +12,27 @@
 //     (Rayon over subquantizers, pq.rs:226-241).
 // The training rows never change, so each rank receives the column slice x[:, its subquantizers] of every other
 // rank ONCE (an all-to-all of the training matrix when the state is created) and keeps both layouts.  Per iteration
-// only the assignments travel (all-to-all of u8 codes, n * M bytes in total) and the new centroids are
-// all-gathered (M * k * dsub floats).  Everything is stream-ordered on the caller's stream.
+// only the assignments travel (n * M bytes in total) and the new centroids are all-gathered (M * k * dsub floats).
+// Everything is stream-ordered on the caller's stream.
+//
+// How the assignments travel: the [M][pitch] code matrix of ALL rows is one virtual address range on every rank
+// whose column block of subquantizer m is physical memory of the rank that owns m (CUDA virtual memory management:
+// cuMemCreate on the owner, exported as a file descriptor, passed over a Unix socket, cuMemMap on every rank).  The
+// assignment kernels of a rank therefore store each code straight into its owner's HBM over NVLink while they run --
+// there is no separate exchange step, no receive buffer and no re-assembly; one tiny all-gather orders "all stores
+// done" before the owners' updates.  When the window cannot be set up (no peer access, descriptors not passable,
+// RB_DIST_P2P=0) the ranks agree to fall back to a grouped ncclSend/Recv of the code blocks.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <sys/socket.h>
+#include <sys/time.h>
+#include <sys/un.h>
+#include <unistd.h>
 
+#include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -102,6 +117,125 @@ const NcclApi &nccl()
         }                                                                                                        \
     } while (0)
 
+
+// CUDA driver entry points for virtual memory management, resolved through the runtime (no link-time libcuda).
+struct DriverApi {
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*MemExport)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImport)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+    CUresult (*MemGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    bool ok = false;
+};
+
+const DriverApi &driver()
+{
+    static DriverApi api = []() {
+        DriverApi a;
+        bool all = true;
+        auto get = [&](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) {
+                (void)cudaGetLastError();
+                all = false;
+            }
+        };
+        get("cuMemCreate", (void **)&a.MemCreate);
+        get("cuMemRelease", (void **)&a.MemRelease);
+        get("cuMemAddressReserve", (void **)&a.MemAddressReserve);
+        get("cuMemAddressFree", (void **)&a.MemAddressFree);
+        get("cuMemMap", (void **)&a.MemMap);
+        get("cuMemUnmap", (void **)&a.MemUnmap);
+        get("cuMemSetAccess", (void **)&a.MemSetAccess);
+        get("cuMemExportToShareableHandle", (void **)&a.MemExport);
+        get("cuMemImportFromShareableHandle", (void **)&a.MemImport);
+        get("cuMemGetAllocationGranularity", (void **)&a.MemGranularity);
+        a.ok = all;
+        return a;
+    }();
+    return api;
+}
+
+constexpr size_t kWindowGranule = (size_t)2 << 20;  // every column of the window starts on a mapping granule
+
+// The code matrix of all rows, [M][pitch] bytes, as one address range; column block [m_lo[r], m_lo[r + 1]) is memory
+// of rank r.
+struct CodeWindow {
+    CUdeviceptr va = 0;
+    size_t va_bytes = 0, pitch = 0;  // pitch: bytes per subquantizer column (a multiple of kWindowGranule)
+    std::vector<CUmemGenericAllocationHandle> handle;  // per rank; 0: none
+    std::vector<char> mapped;
+    bool active = false;
+};
+
+void window_release(CodeWindow &w, const std::vector<size_t> &m_lo)
+{
+    const DriverApi &d = driver();
+    if (!d.ok) return;
+    for (size_t r = 0; r < w.handle.size(); r++) {
+        if (w.mapped.size() > r && w.mapped[r]) d.MemUnmap(w.va + m_lo[r] * w.pitch, (m_lo[r + 1] - m_lo[r]) * w.pitch);
+        if (w.handle[r]) d.MemRelease(w.handle[r]);
+    }
+    if (w.va) d.MemAddressFree(w.va, w.va_bytes);
+    w = CodeWindow();
+}
+
+// abstract-namespace datagram sockets carry the exported descriptors between the ranks of one node
+socklen_t window_addr(sockaddr_un *a, unsigned long long token, int rank)
+{
+    memset(a, 0, sizeof(*a));
+    a->sun_family = AF_UNIX;
+    const int len = snprintf(a->sun_path + 1, sizeof(a->sun_path) - 1, "rbw-%016llx-%d", token, rank);
+    return (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + (size_t)len);
+}
+
+bool send_fd(int sock, unsigned long long token, int to_rank, int my_rank, int fd)
+{
+    sockaddr_un to;
+    const socklen_t to_len = window_addr(&to, token, to_rank);
+    int payload = my_rank;
+    iovec iov{&payload, sizeof(payload)};
+    alignas(cmsghdr) char ctrl[CMSG_SPACE(sizeof(int))];
+    memset(ctrl, 0, sizeof(ctrl));
+    msghdr msg{};
+    msg.msg_name = &to;
+    msg.msg_namelen = to_len;
+    msg.msg_iov = &iov;
+    msg.msg_iovlen = 1;
+    msg.msg_control = ctrl;
+    msg.msg_controllen = sizeof(ctrl);
+    cmsghdr *cm = CMSG_FIRSTHDR(&msg);
+    cm->cmsg_level = SOL_SOCKET;
+    cm->cmsg_type = SCM_RIGHTS;
+    cm->cmsg_len = CMSG_LEN(sizeof(int));
+    memcpy(CMSG_DATA(cm), &fd, sizeof(int));
+    return sendmsg(sock, &msg, 0) == (ssize_t)sizeof(payload);
+}
+
+bool recv_fd(int sock, int *from_rank, int *fd)
+{
+    int payload = -1;
+    iovec iov{&payload, sizeof(payload)};
+    alignas(cmsghdr) char ctrl[CMSG_SPACE(sizeof(int))];
+    memset(ctrl, 0, sizeof(ctrl));
+    msghdr msg{};
+    msg.msg_iov = &iov;
+    msg.msg_iovlen = 1;
+    msg.msg_control = ctrl;
+    msg.msg_controllen = sizeof(ctrl);
+    if (recvmsg(sock, &msg, 0) != (ssize_t)sizeof(payload)) return false;
+    cmsghdr *cm = CMSG_FIRSTHDR(&msg);
+    if (!cm || cm->cmsg_level != SOL_SOCKET || cm->cmsg_type != SCM_RIGHTS) return false;
+    memcpy(fd, CMSG_DATA(cm), sizeof(int));
+    *from_rank = payload;
+    return true;
+}
+
 rb_status require_nccl()
 {
     if (!nccl().ok) {
@@ -135,10 +269,134 @@ struct rb_kmeans_dist {
     float *packed_own = nullptr, *loss_all = nullptr;
     double *sumsq_own = nullptr;  // sum ||x_m||^2 of the owned subquantizers over all rows (FP64, computed once)
     float *slabs = nullptr;       // streaming update: the owned columns as subquantizer-major slabs (then xcol is dropped)
+    CodeWindow win;               // peer-mapped code matrix (active: assignments are stored straight into their owners' memory)
+    unsigned long long *sync_dev = nullptr;  // [W + 1]: scratch of the tiny all-gathers
     int code_width = 1;
     size_t pitch_local = 0, pitch_total = 0;
     size_t m_own() const { return m_lo[c->rank + 1] - m_lo[c->rank]; }
 };
+
+namespace {
+
+// every rank contributes one 64-bit value and learns all of them (doubles as a barrier of the ranks' streams)
+rb_status exchange_u64(rb_kmeans_dist *h, cudaStream_t st, unsigned long long mine, std::vector<unsigned long long> &all)
+{
+    const int W = h->c->world;
+    RB_CUDA_TRY(cudaMemcpyAsync(h->sync_dev + W, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    RB_NCCL_TRY(nccl().AllGather(h->sync_dev + W, h->sync_dev, 1, ncclUint64, h->c->comm, st));
+    all.assign(W, 0);
+    RB_CUDA_TRY(cudaMemcpyAsync(all.data(), h->sync_dev, (size_t)W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RB_CUDA_TRY(cudaStreamSynchronize(st));
+    return RB_OK;
+}
+
+// Builds the peer-mapped code matrix (see the file header).  Collective.  Any local failure is voted on, so that either
+// every rank ends with win.active or none does; only a failing collective is an error.
+rb_status window_setup(rb_kmeans_dist *h, cudaStream_t st)
+{
+    const int W = h->c->world, me = h->c->rank;
+    const size_t M = h->M, cw = (size_t)h->code_width, m_own = h->m_own();
+    CodeWindow &w = h->win;
+    const DriverApi &d = driver();
+    const char *env = getenv("RB_DIST_P2P");
+    bool ok = d.ok && !(env && env[0] == '0');
+    w.pitch = ceil_div(h->pitch_total * cw, kWindowGranule) * kWindowGranule;
+    w.handle.assign(W, 0);
+    w.mapped.assign(W, 0);
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = h->c->device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    int my_fd = -1, sock = -1;
+    if (ok) {
+        size_t g = 0;
+        ok = d.MemGranularity(&g, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) == CUDA_SUCCESS && g != 0 && kWindowGranule % g == 0;
+    }
+    if (ok && m_own) {
+        ok = d.MemCreate(&w.handle[me], m_own * w.pitch, &prop, 0) == CUDA_SUCCESS;
+        if (!ok) w.handle[me] = 0;
+        if (ok) ok = d.MemExport(&my_fd, w.handle[me], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+    }
+    // a socket name nobody else uses: rank 0's random token
+    unsigned long long token = 0;
+    if (me == 0) {
+        FILE *f = fopen("/dev/urandom", "rb");
+        if (!f || fread(&token, sizeof(token), 1, f) != 1) token = ((unsigned long long)getpid() << 32) ^ (unsigned long long)clock();
+        if (f) fclose(f);
+    }
+    std::vector<unsigned long long> all;
+    RB_TRY(exchange_u64(h, st, token, all));
+    token = all[0];
+    if (ok) {
+        sock = socket(AF_UNIX, SOCK_DGRAM | SOCK_CLOEXEC, 0);
+        sockaddr_un a;
+        const socklen_t alen = window_addr(&a, token, me);
+        timeval tv{20, 0};
+        ok = sock >= 0 && bind(sock, reinterpret_cast<sockaddr *>(&a), alen) == 0 &&
+             setsockopt(sock, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv)) == 0;
+    }
+    RB_TRY(exchange_u64(h, st, ok ? 1ull : 0ull, all));  // everyone is bound (or someone gave up)
+    bool go = true;
+    for (int r = 0; r < W; r++) go = go && all[r] != 0;
+    if (go) {
+        if (m_own)
+            for (int r = 0; r < W && ok; r++)
+                if (r != me) ok = send_fd(sock, token, r, me, my_fd);
+        for (int r = 0; r < W && ok; r++) {
+            if (r == me || h->m_lo[r + 1] == h->m_lo[r]) continue;  // one descriptor from every other owner, any order
+            int from = -1, fd = -1;
+            if (!recv_fd(sock, &from, &fd)) {
+                ok = false;
+                break;
+            }
+            if (from < 0 || from >= W || from == me || w.handle[from] != 0) {
+                close(fd);
+                ok = false;
+                break;
+            }
+            ok = d.MemImport(&w.handle[from], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+            if (!ok) w.handle[from] = 0;
+            close(fd);
+        }
+        if (ok) {
+            w.va_bytes = M * w.pitch;
+            ok = d.MemAddressReserve(&w.va, w.va_bytes, kWindowGranule, 0, 0) == CUDA_SUCCESS;
+            if (!ok) w.va = 0;
+        }
+        for (int r = 0; r < W && ok; r++) {
+            const size_t mr = h->m_lo[r + 1] - h->m_lo[r];
+            if (!mr) continue;
+            ok = d.MemMap(w.va + h->m_lo[r] * w.pitch, mr * w.pitch, 0, w.handle[r], 0) == CUDA_SUCCESS;
+            if (ok) w.mapped[r] = 1;
+        }
+        if (ok) {
+            CUmemAccessDesc acc;
+            memset(&acc, 0, sizeof(acc));
+            acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+            acc.location.id = h->c->device;
+            acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+            ok = d.MemSetAccess(w.va, w.va_bytes, &acc, 1) == CUDA_SUCCESS;  // peers' memory: needs P2P between the devices
+        }
+        if (ok && m_own)
+            ok = cudaMemsetAsync(reinterpret_cast<void *>(w.va + h->m_lo[me] * w.pitch), 0, m_own * w.pitch, st) == cudaSuccess;
+    }
+    if (my_fd >= 0) close(my_fd);
+    if (sock >= 0) close(sock);
+    RB_TRY(exchange_u64(h, st, (go && ok) ? 1ull : 0ull, all));
+    bool active = true;
+    for (int r = 0; r < W; r++) active = active && all[r] != 0;
+    if (!active) {
+        (void)cudaGetLastError();
+        window_release(w, h->m_lo);
+    } else {
+        w.active = true;
+    }
+    return RB_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -225,6 +483,11 @@ void rb_kmeans_dist_destroy(rb_kmeans_dist *h)
     cudaFree(h->loss_all);
     cudaFree(h->sumsq_own);
     cudaFree(h->slabs);
+    cudaFree(h->sync_dev);
+    if (h->win.va || !h->win.handle.empty()) {
+        cudaDeviceSynchronize();  // nothing may still be storing into the window
+        window_release(h->win, h->m_lo);
+    }
     delete h;
 }
 
@@ -287,7 +550,7 @@ rb_status rb_kmeans_dist_create(rb_comm *c, const float *x_local, size_t n_local
         size_t recv_bytes = 0;
         for (int r = 0; r < W; r++) recv_bytes += m_own * rb_kmeans_code_pitch(h->n_of[r]) * cw;
         const bool stream_upd = kmeans_stream_enabled() && cw == 1 && stream_update_supported(k, dsub);
-        RB_CUDA_TRY(cudaMalloc(&h->codes_local, M * h->pitch_local * cw + 16));
+        if (W == 1) RB_CUDA_TRY(cudaMalloc(&h->codes_local, M * h->pitch_local * cw + 16));
         RB_CUDA_TRY(cudaMalloc(&h->packed_own, (rb_kmeans_packed_len(m_own ? m_own : 1, k, dsub)) * sizeof(float)));
         RB_CUDA_TRY(cudaMalloc(&h->loss_all, M * sizeof(float)));
         RB_CUDA_TRY(cudaMalloc(&h->sumsq_own, (m_own ? m_own : 1) * sizeof(double)));
@@ -301,9 +564,14 @@ rb_status rb_kmeans_dist_create(rb_comm *c, const float *x_local, size_t n_local
             return RB_OK;
         }
         RB_CUDA_TRY(cudaMalloc(&h->xcol, (h->n_total * dcols + 4) * sizeof(float)));
-        RB_CUDA_TRY(cudaMalloc(&h->codes_recv, recv_bytes + 16));
-        RB_CUDA_TRY(cudaMalloc(&h->codes_own, m_own * h->pitch_total * cw + 16));
-        RB_CUDA_TRY(cudaMemsetAsync(h->codes_own, 0, m_own * h->pitch_total * cw + 16, st));
+        RB_CUDA_TRY(cudaMalloc(&h->sync_dev, (size_t)(W + 1) * sizeof(unsigned long long)));
+        RB_TRY(window_setup(h, st));
+        if (!h->win.active) {  // exchange by ncclSend/Recv: local assignments, receive blocks, assembled own columns
+            RB_CUDA_TRY(cudaMalloc(&h->codes_local, M * h->pitch_local * cw + 16));
+            RB_CUDA_TRY(cudaMalloc(&h->codes_recv, recv_bytes + 16));
+            RB_CUDA_TRY(cudaMalloc(&h->codes_own, m_own * h->pitch_total * cw + 16));
+            RB_CUDA_TRY(cudaMemsetAsync(h->codes_own, 0, m_own * h->pitch_total * cw + 16, st));
+        }
         // one-time all-to-all of the training matrix: rank s receives x[rows of r, columns of s] from every r
         float *sendbuf = nullptr;
         RB_CUDA_TRY(pool_malloc((void **)&sendbuf, (n_local * h->d + 4) * sizeof(float), st));
@@ -363,7 +631,17 @@ rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *h, float *centroids, float *los
     const size_t M = h->M, k = h->k, dsub = h->dsub, cw = (size_t)h->code_width;
     const size_t m_own = h->m_own(), dcols = m_own * dsub;
     // 1. cluster_assignments of the local rows against all M codebooks (kmeans.rs:319)
-    RB_TRY(rb_kmeans_assign(h->x_local, h->n_local, h->ldx, centroids, M, k, dsub, h->codes_local, stream));
+    const bool window = W > 1 && h->win.active;
+    if (window) {
+        // ... stored straight into the owners' memory: this rank's rows of every column of the peer-mapped matrix
+        unsigned char *base = reinterpret_cast<unsigned char *>(h->win.va);
+        RB_TRY(kmeans_assign_strided(h->x_local, h->n_local, h->ldx, centroids, M, k, dsub, base + h->row_off[me] * cw,
+                                     (ptrdiff_t)(h->win.pitch / cw), st));
+        // every rank's stores are complete once all ranks have passed this point of their streams
+        RB_NCCL_TRY(nccl().AllGather(h->sync_dev + W, h->sync_dev, 1, ncclUint64, c->comm, st));
+    } else {
+        RB_TRY(rb_kmeans_assign(h->x_local, h->n_local, h->ldx, centroids, M, k, dsub, h->codes_local, stream));
+    }
     // 2. the assignments of subquantizers [m_lo[s], m_lo[s+1]) go to rank s (column-major blocks are contiguous)
     const unsigned char *codes_own = h->codes_own;
     size_t pitch_own = h->pitch_total;
@@ -374,6 +652,9 @@ rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *h, float *centroids, float *los
         pitch_own = h->pitch_local;
         x_own = h->x_local;
         ld_own = h->ldx;
+    } else if (window) {  // the owned columns of the window are local memory and already complete
+        codes_own = reinterpret_cast<const unsigned char *>(h->win.va) + h->m_lo[me] * h->win.pitch;
+        pitch_own = h->win.pitch / cw;
     } else {
     std::vector<unsigned char *> recv_at(W);
     {
@@ -451,6 +732,8 @@ rb_status rb_kmeans_dist_iterate(rb_kmeans_dist *h, float *centroids, float *los
         RB_CUDA_TRY(cudaMemcpyAsync(loss_or_null, h->loss_all, M * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return RB_OK;
 }
+
+int rb_kmeans_dist_peer_window(const rb_kmeans_dist *h) { return h && h->win.active ? 1 : 0; }
 
 rb_status rb_pq_train_dist(rb_comm *c, const float *instances_local, size_t n_local, size_t n_total, size_t d,
                            ptrdiff_t row_stride, size_t n_subquantizers, uint32_t n_subquantizer_bits, size_t n_iterations,

@@ -164,6 +164,12 @@ class ShardedKMeans:
         check(lib.rb_kmeans_dist_iterate(self._h, centroids.data_ptr(), None if loss is None else loss.data_ptr(),
                                          torch.cuda.current_stream().cuda_stream))
 
+    @property
+    def peer_window(self) -> bool:
+        """True: the assignment kernels store the codes straight into their owners' memory (peer-mapped code matrix);
+        False: the codes travel by ncclSend/Recv (or there is one rank)."""
+        return bool(lib.rb_kmeans_dist_peer_window(self._h))
+
     def close(self) -> None:
         if self._h:
             import torch

@@ -57,6 +57,8 @@ torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda", dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 res = {"sharded": (cen, t.item())}
+if rank == 0:
+    print(f"code exchange: {'peer-mapped window (stores into the owners\' memory)' if km.peer_window else 'ncclSend/Recv'}", flush=True)
 km.close()
 
 if legacy:
