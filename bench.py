@@ -347,6 +347,7 @@ def run_ours(args) -> None:
     it_bytes = n3 * (2 * 4 * M3 * dsub3 + 2 * M3)
     it_gbs = it_bytes / (it_ms * 1e-3) / 1e9 / world
     bit_identical = None
+    peer_window = km.peer_window
     km.close()
     if world > 1:
         same_everywhere = cen3.view(torch.int32).clone()
@@ -381,6 +382,8 @@ def run_ours(args) -> None:
         "bit_identity_checked_against": "a one-GPU run of the same rows through rb_kmeans_assign_accumulate / rb_kmeans_finalize "
                                         "(sort + chain kernels)",
         "exchange_bytes_per_iter": (n3 * M3 + 4 * M3 * K_CENTROIDS * dsub3 * world) if world > 1 else 0,
+        "code_exchange": ("peer-mapped code matrix: the assignment kernels store into the owners' HBM over NVLink" if peer_window
+                          else "ncclSend/Recv") if world > 1 else "none (one rank)",
         "roofline": {"bound": "hbm", "achieved": it_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s per GPU",
                      "frac": it_gbs / peaks["hbm_gbs"],
                      "algorithmic_bytes_per_iter": it_bytes, "note": "two passes over x (assign, update) + codes"}}
@@ -441,6 +444,29 @@ def run_ours(args) -> None:
     del rec4, c4
 
     log("C4 done")
+    # the caller-side quantized storage over the C2 codes (2M x 30 u8 + norms resident in HBM):
+    # fused decode + dot of 8 / 64 queries against every stored row (rb_qstore_dot)
+    store = rb.QuantizedArray(pq, codes, torch.rand((N_ROWS,), device=dev) + 0.5)
+    dd = {}
+    for nq in (8, 64):
+        qs = torch.randn((nq, D), device=dev)
+        sc = torch.empty((nq, N_ROWS), device=dev)
+        store.dot(qs, sc)
+        barrier()
+        k0.record(stream)
+        for _ in range(3):
+            store.dot(qs, sc)
+        k1.record(stream)
+        barrier()
+        ms = k0.elapsed_time(k1) / 3
+        dd[f"nq{nq}"] = {"ms": ms, "scores_per_s": world * nq * N_ROWS / (ms * 1e-3),
+                         "hbm_bytes": (nq // 8) * N_ROWS * M + nq * N_ROWS * 4,
+                         "hbm_gbs": ((nq // 8) * N_ROWS * M + nq * N_ROWS * 4) / (ms * 1e-3) / 1e9}
+        del sc
+    extra["decode_dot"] = {"workload": "QuantizedArray.dot: queries x (2M rows x 30 u8 codes, norms) per GPU, scores in f32; "
+                                       "bound by shared-memory table lookups (30 per row and query), not by HBM", **dd}
+    store.close()
+    log("decode + dot done")
     if rank == 0:
         # roofline of the dominant kernel (the encode kernel is the whole step): algorithmic bytes per vector
         # = 4*d + M, against the measured HBM copy bandwidth — at the measured peaks the HBM bound

@@ -33,6 +33,26 @@ def test_multi_gpu_training_is_bit_identical_to_one_gpu(oracle, n, M, bits, dsub
     assert np.array_equal(one.subquantizers().view(np.int32), want.view(np.int32))
 
 
+def test_code_exchange_modes_agree(monkeypatch):
+    """The assignments reach their owners either through the peer-mapped code matrix (stores into the owners' memory)
+    or, RB_DIST_P2P=0, by ncclSend/Recv: the trained quantizer is the same bit for bit."""
+    import reductive_b200 as rb
+
+    devs = _devices()
+    if len(devs) < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n, M, bits, dsub = 30_011, 12, 8, 8
+    x = normal((n, M * dsub), 51)
+    init = rows_as_initial_centroids(x, M, 1 << bits, 52)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RB_DIST_P2P", mode)
+        got[mode] = rb.Pq.train_pq_using(M, bits, 5, 1, x, None, initial_centroids=init, devices=devs).subquantizers()
+    assert np.array_equal(got["1"].view(np.int32), got["0"].view(np.int32))
+    one = rb.Pq.train_pq_using(M, bits, 5, 1, x, None, initial_centroids=init).subquantizers()
+    assert np.array_equal(got["1"].view(np.int32), one.view(np.int32))
+
+
 def test_multi_gpu_training_more_devices_than_subquantizers():
     import reductive_b200 as rb
 
