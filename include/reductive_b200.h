@@ -222,6 +222,10 @@ rb_status rb_project_rows(const float *x, size_t n, size_t d, ptrdiff_t x_row_st
 
 /* ---- Opq / GaussianOpq training (opq.rs:46-209, gaussian_opq.rs:33-68) ------------------------------ */
 
+/* Gram matrices of Opq training (rb_covariance, the X^T.Y^ of rb_opq_train_iteration): 0 = auto (tensor cores for
+ * n >= 4096 rows and 16 <= d <= 512, FP32 CUDA cores otherwise), 1 = FP32 CUDA cores, 2 = tensor cores (UNSUPPORTED
+ * outside that range).  Both are within 1e-5 of the exact product relative to its largest element. */
+rb_status rb_set_gram_algo(int algo);
 /* Covariance::covariance over observation axis 0 (linalg.rs:23-44) of x [n, d] (DEVICE, row stride x_row_stride):
  * cov_out DEVICE [d, d].  RB_ERR_SHAPE for n == 0 (the reference asserts).  The d x d eigendecomposition that
  * follows in Opq::create_projection_matrix (opq.rs:120-135) stays on host LAPACK, as in the reference. */

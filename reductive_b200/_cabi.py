@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = [
     "rb_kmeans_finalize", "rb_pq_train", "rb_project_rows",
     "rb_dist_subquantizer_range", "rb_comm_unique_id", "rb_comm_create", "rb_comm_destroy", "rb_comm_rank",
     "rb_comm_world", "rb_kmeans_dist_create", "rb_kmeans_dist_iterate", "rb_kmeans_dist_destroy", "rb_kmeans_dist_peer_window", "rb_pq_train_dist",
-    "rb_pq_train_multi", "rb_covariance", "rb_opq_train_iteration", "rb_pq_create_f64", "rb_pq_quantize_batch_f64", "rb_pq_reconstruct_batch_f64", "rb_pq_train_f64",
+    "rb_pq_train_multi", "rb_set_gram_algo", "rb_covariance", "rb_opq_train_iteration", "rb_pq_create_f64", "rb_pq_quantize_batch_f64", "rb_pq_reconstruct_batch_f64", "rb_pq_train_f64",
     "rb_qstore_create", "rb_qstore_destroy", "rb_qstore_len", "rb_qstore_has_norms", "rb_qstore_embeddings", "rb_qstore_dot",
 ]
 
@@ -166,6 +166,7 @@ def _load() -> C.CDLL:
     lib.rb_pq_train.argtypes = [fp, sz, sz, pd, pd, sz, C.c_uint32, sz, sz, fp, fp, C.c_int, vp, C.POINTER(vp)]
     lib.rb_project_rows.argtypes = [fp, sz, sz, pd, pd, fp, C.c_int, fp, vp]
     lib.rb_covariance.argtypes = [fp, sz, sz, pd, fp, vp]
+    lib.rb_set_gram_algo.argtypes = [C.c_int]
     lib.rb_opq_train_iteration.argtypes = [fp, sz, sz, pd, fp, fp, sz, sz, fp, vp]
     lib.rb_dist_subquantizer_range.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
     lib.rb_comm_unique_id.argtypes = [vp, sz]
@@ -230,6 +231,15 @@ def release_scratch() -> None:
 def set_project_algo(algo: int) -> None:
     """PROJECT_AUTO / PROJECT_EXACT (reference-order FP32 GEMM) / PROJECT_TENSOR (tcgen05, codes still bit-exact)."""
     check(lib.rb_set_project_algo(algo))
+
+
+GRAM_AUTO, GRAM_CUDA_CORES, GRAM_TENSOR = 0, 1, 2
+
+
+def set_gram_algo(algo: int) -> None:
+    """Gram matrices of Opq training: GRAM_AUTO (tensor cores for n >= 4096, 16 <= d <= 512), GRAM_CUDA_CORES (FP32
+    FMA), GRAM_TENSOR (tcgen05, two-limb BF16; UNSUPPORTED outside its range)."""
+    check(lib.rb_set_gram_algo(algo))
 
 
 def set_kmeans_update(ordered) -> None:

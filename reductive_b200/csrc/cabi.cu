@@ -1121,6 +1121,13 @@ rb_status rb_pq_train(const float *instances, size_t n, size_t d, ptrdiff_t rs, 
 }
 
 // ---- Opq training --------------------------------------------------------------------------------------------------
+rb_status rb_set_gram_algo(int algo)
+{
+    if (algo < 0 || algo > 2) return fail(RB_ERR_INVALID, "gram algo must be 0 (auto), 1 (CUDA cores) or 2 (tensor cores)");
+    set_gram_algo(algo);
+    return RB_OK;
+}
+
 rb_status rb_covariance(const float *x, size_t n, size_t d, ptrdiff_t ldx, float *cov_out, void *stream)
 {
     if (!x || !cov_out) return fail(RB_ERR_INVALID, "NULL argument");

@@ -269,6 +269,12 @@ rb_status launch_qstore_dot(const uint8_t *codes, size_t n, const float *cent, s
                             const float *qrot, size_t nq, const float *norms, float *lut, float *out, ptrdiff_t out_ld,
                             cudaStream_t stream);
 
+// gram_tc.cu -- the same Gram matrix on tcgen05 (two-limb BF16 operands, FP32 accumulation in segments of 2048 rows)
+bool gram_tensor_supported(const float *a, ptrdiff_t lda, const float *b, ptrdiff_t ldb, size_t n, size_t da, size_t db);
+rb_status launch_gram_tensor(const float *a, ptrdiff_t lda, const float *b, ptrdiff_t ldb, size_t n, size_t da, size_t db,
+                             const float *a_sub, const float *b_sub, float b_div, float *out, cudaStream_t stream);
+void set_gram_algo(int algo);
+
 // Streaming ordered update for training loops (kmeans.cu): x laid out once as subquantizer-major slabs
 // (slab_floats(n, d) floats), then per iteration one pass that streams the slabs; sums bit-identical to the chain path.
 bool stream_update_supported(size_t k, size_t dsub);

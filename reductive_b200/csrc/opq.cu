@@ -5,11 +5,14 @@
 //           Opq::train_iteration       src/pq/opq.rs:161-189  (rb_opq_train_iteration in cabi.cu drives these kernels
 //                                                              together with the projection, k-means and encode ones)
 // The d x d eigendecomposition / SVD stay on host LAPACK as in the reference (opq.rs:123,187; north_star).
+// Large Gram matrices (n >= 4096, 16 <= d <= 512) run on the tensor cores (gram_tc.cu); the kernel below serves the rest.
 //
 // gram_kernel: out[i, j] = sum_r (a[r, i] - a_sub[i]) * ((b[r, j] - b_sub[j]) / b_div).  Reduction over the n rows is
 // split over the grid's z dimension into per-split partial matrices that a second kernel adds IN ORDER (deterministic;
 // no float atomics).  FP32 FMA on CUDA cores: 2 n d^2 flop, not on the hot path (training only); a 64 x 64 output
 // tile per block, 4 x 4 outputs per thread, both operand tiles staged through shared memory with coalesced row reads.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace rb {
@@ -116,10 +119,20 @@ rb_status launch_column_means(const float *x, size_t n, size_t d, ptrdiff_t ldx,
     return RB_OK;
 }
 
+static std::atomic<int> g_gram_algo{0};  // rb_set_gram_algo: 0 auto, 1 FP32 CUDA cores, 2 tensor cores (gram_tc.cu)
+void set_gram_algo(int algo) { g_gram_algo.store(algo); }
+
 rb_status launch_gram(const float *a, ptrdiff_t lda, const float *b, ptrdiff_t ldb, size_t n, size_t da, size_t db,
                       const float *a_sub, const float *b_sub, float b_div, float *out, cudaStream_t stream)
 {
     if (da == 0 || db == 0) return RB_OK;
+    const int algo = g_gram_algo.load();
+    const bool tc_ok = gram_tensor_supported(a, lda, b, ldb, n, da, db);
+    if (algo == 2 && !tc_ok) {
+        set_error("tensor-core Gram does not cover this call (n=%zu, %zu x %zu)", n, da, db);
+        return RB_ERR_UNSUPPORTED;
+    }
+    if (algo != 1 && tc_ok) return launch_gram_tensor(a, lda, b, ldb, n, da, db, a_sub, b_sub, b_div, out, stream);
     const size_t tiles = ceil_div(da, (size_t)kGT) * ceil_div(db, (size_t)kGT);
     // enough row splits to fill the GPU a few times over, at least 4096 rows each
     size_t splits = ceil_div((size_t)sm_count() * 4, tiles);

@@ -629,6 +629,39 @@ def test_covariance_matches_the_oracle(oracle, torch_cuda):  # linalg.rs:23-44, 
     assert np.array_equal(got, got.T) or np.abs(got - got.T).max() <= 1e-6 * np.abs(got).max()
 
 
+@pytest.mark.parametrize("n,d,pad", [(50_000, 300, 0), (5_000, 64, 0), (20_001, 512, 0), (9_000, 137, 3), (4_096, 390, 0),
+                                     (300_000, 96, 0), (7_777, 16, 5)])
+def test_tensor_core_gram_matches_float64(torch_cuda, n, d, pad):
+    """gram_tc.cu (rb_set_gram_algo(2)): the centred Gram matrix over the rows on tcgen05 -- two-limb BF16 operands,
+    FP32 accumulation in 2048-row segments -- against the float64 product, and beside the FP32 CUDA-core kernel.  Both
+    are held to 1e-5 of the largest element (the tolerance of rb_covariance / X^T.Y^).  Widths cover one and several
+    128-column tiles, one and two MMA column blocks, widths that are no multiple of 16, and padded rows."""
+    torch = torch_cuda
+    from reductive_b200._cabi import GRAM_AUTO, GRAM_CUDA_CORES, GRAM_TENSOR, check, lib, set_gram_algo
+
+    rng = np.random.default_rng(n + d)
+    a = (rng.normal(size=(n, d + pad)) * np.linspace(0.2, 4, d + pad) + np.linspace(-3, 3, d + pad)).astype(F)
+    a[:, 1] += 0.5 * a[:, 0]  # some real off-diagonal mass
+    ad = torch.from_numpy(a).cuda()
+    c = a[:, :d].astype(np.float64) - a[:, :d].mean(0, dtype=np.float64)
+    want = c.T @ c / (n - 1)
+
+    def cov(algo):
+        set_gram_algo(algo)
+        try:
+            out = torch.empty((d, d), device="cuda")
+            check(lib.rb_covariance(ad.data_ptr(), n, d, ad.stride(0), out.data_ptr(), None))
+            return out.cpu().numpy()
+        finally:
+            set_gram_algo(GRAM_AUTO)
+
+    got_tc, got_cc = cov(GRAM_TENSOR), cov(GRAM_CUDA_CORES)
+    scale = np.abs(want).max()
+    assert np.abs(got_tc - want).max() <= 1e-5 * scale, np.abs(got_tc - want).max() / scale
+    assert np.abs(got_cc - want).max() <= 1e-5 * scale
+    assert np.abs(got_tc - got_tc.T).max() <= 4e-6 * scale
+
+
 @pytest.mark.parametrize("n,M,k,dsub", [(6_000, 4, 16, 6), (20_000, 8, 256, 8)])
 def test_opq_train_iteration_matches_the_oracle(oracle, torch_cuda, n, M, k, dsub):
     """Opq::train_iteration (opq.rs:161-189) from identical projection and centroids: the k-means step is bit-identical
