@@ -138,24 +138,23 @@ __global__ void __launch_bounds__(kGmThreads, 1) gram_mma_kernel(const __grid_co
 
     if (warp == 0) {
         // ===================== producer: bulk copies of the limb slices into the operand layout =====================
-        if (lane == 0) {
-            for (long long t = 0; t < n_steps; t++) {
-                const int s = (int)(t % p.stages);
-                mbar_wait(&empty[s], (uint32_t)(((t / p.stages) & 1) ^ 1));
-                unsigned char *st = stages + (size_t)s * stage_bytes;
-                mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
-                const long long g = 2 * (t0 + t);
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const size_t oa = (size_t)(g + q) * p.dpad_a + i0, ob = (size_t)(g + q) * p.dpad_b + j0;
-                    bulk_g2s(st + q * 2048, p.a_hi + oa, 2048, &full[s]);
-                    bulk_g2s(st + a_limb + q * 2048, p.a_lo + oa, 2048, &full[s]);
-                    bulk_g2s(st + 2 * a_limb + q * nw * 16, p.b_hi + ob, (uint32_t)nw * 16, &full[s]);
-                    bulk_g2s(st + 2 * a_limb + b_limb + q * nw * 16, p.b_lo + ob, (uint32_t)nw * 16, &full[s]);
-                }
-            }
+        // lanes 0-7 issue one copy each (a single thread issuing all eight was the bottleneck: ~1 100 clk per stage);
+        // lane 0 also posts the byte count -- a copy that completes before the count is posted only drives the
+        // transaction count negative for a moment, the phase cannot complete before lane 0's arrival
+        const int q = (lane >> 2) & 1, kind = lane & 3;  // row group of the stage, (A hi, A lo, B hi, B lo)
+        const uint4 *src = kind == 0 ? p.a_hi : kind == 1 ? p.a_lo : kind == 2 ? p.b_hi : p.b_lo;
+        const size_t pitch = kind < 2 ? (size_t)p.dpad_a : (size_t)p.dpad_b;
+        const size_t col = kind < 2 ? (size_t)i0 : (size_t)j0;
+        const uint32_t bytes = kind < 2 ? 2048u : (uint32_t)nw * 16u;
+        const int dst_off = (kind == 0 ? 0 : kind == 1 ? a_limb : kind == 2 ? 2 * a_limb : 2 * a_limb + b_limb) + q * (int)bytes;
+        for (long long t = 0; t < n_steps; t++) {
+            const int s = (int)(t % p.stages);
+            mbar_wait(&empty[s], (uint32_t)(((t / p.stages) & 1) ^ 1));
+            unsigned char *st = stages + (size_t)s * stage_bytes;
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+            if (lane < 8) bulk_g2s(st + dst_off, src + (size_t)(2 * (t0 + t) + q) * pitch + col, bytes, &full[s]);
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = idesc_f16(128, (uint32_t)nw, 1);

@@ -22,25 +22,38 @@ constexpr int kGT = 64;    // output tile edge
 constexpr int kGR = 32;    // rows per shared-memory step
 
 __global__ void __launch_bounds__(256)
-column_sum_partial_kernel(const float *__restrict__ x, long long n, long long ldx, int d, int n_splits, double *__restrict__ partial)
+column_sum_partial_kernel(const float *__restrict__ x, long long n, long long ldx, int d, long long rows_per_split,
+                          double *__restrict__ partial)
 {
-    // block (column tile of 256 columns, split): fixed row range, FP64 running sums, fixed order
+    // block (column tile of 256 columns, row split): fixed row range, FP64 running sum per column, fixed order; eight
+    // independent (coalesced) row loads in flight per thread
     const int col = blockIdx.x * 256 + threadIdx.x;
-    const long long per = (n + n_splits - 1) / n_splits;
-    const long long r0 = (long long)blockIdx.y * per, r1 = min(n, r0 + per);
+    const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(n, r0 + rows_per_split);
     if (col >= d) return;
     double acc = 0.0;
-    for (long long r = r0; r < r1; r++) acc += (double)__ldg(x + r * ldx + col);
+    long long r = r0;
+    for (; r + 8 <= r1; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = __ldg(x + (r + e) * ldx + col);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc += (double)v[e];
+    }
+    for (; r < r1; r++) acc += (double)__ldg(x + r * ldx + col);
     partial[(size_t)blockIdx.y * d + col] = acc;
 }
 
-__global__ void column_mean_final_kernel(const double *__restrict__ partial, int d, int n_splits, double inv_n, float *__restrict__ means)
+__global__ void __launch_bounds__(256)
+column_mean_final_kernel(const double *__restrict__ partial, int d, int n_splits, double inv_n, float *__restrict__ means)
 {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per column: lane l adds the splits l, l + 32, ... in order, then a fixed shuffle tree (deterministic)
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (col >= d) return;
     double s = 0.0;
-    for (int p = 0; p < n_splits; p++) s += partial[(size_t)p * d + col];
-    means[col] = (float)(s * inv_n);
+    for (int p = lane; p < n_splits; p += 32) s += partial[(size_t)p * d + col];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) means[col] = (float)(s * inv_n);
 }
 
 __global__ void __launch_bounds__(256)
@@ -108,12 +121,16 @@ __global__ void gram_final_kernel(const float *__restrict__ partial, size_t len,
 rb_status launch_column_means(const float *x, size_t n, size_t d, ptrdiff_t ldx, float *means, cudaStream_t stream)
 {
     if (n == 0 || d == 0) return RB_OK;
-    const int splits = 64;
+    // row splits of at least 512 rows, enough of them to fill the GPU (the sums of a split and the order in which the
+    // splits are added are fixed: deterministic)
+    size_t rows_per_split = 512;
+    if (ceil_div(n, rows_per_split) > 4096) rows_per_split = ceil_div(n, (size_t)4096);
+    const int splits = (int)ceil_div(n, rows_per_split);
     double *partial = nullptr;
     RB_CUDA_TRY(pool_malloc((void **)&partial, (size_t)splits * d * sizeof(double), stream));
-    column_sum_partial_kernel<<<dim3((unsigned)ceil_div(d, 256), splits), 256, 0, stream>>>(x, (long long)n, (long long)ldx, (int)d,
-                                                                                            splits, partial);
-    column_mean_final_kernel<<<(unsigned)ceil_div(d, 128), 128, 0, stream>>>(partial, (int)d, splits, 1.0 / (double)n, means);
+    column_sum_partial_kernel<<<dim3((unsigned)ceil_div(d, (size_t)256), (unsigned)splits), 256, 0, stream>>>(
+        x, (long long)n, (long long)ldx, (int)d, (long long)rows_per_split, partial);
+    column_mean_final_kernel<<<(unsigned)ceil_div(d, (size_t)8), 256, 0, stream>>>(partial, (int)d, splits, 1.0 / (double)n, means);
     cudaFreeAsync(partial, stream);
     RB_LAUNCH_CHECK();
     return RB_OK;
