@@ -444,6 +444,31 @@ def run_ours(args) -> None:
     del rec4, c4
 
     log("C4 done")
+    # the device parts of Opq training on the C4 shape -- the covariance of the PCA init
+    # (linalg.rs:23-44) and one train_iteration without its d x d SVD (opq.rs:161-189)
+    from reductive_b200._cabi import check as _check, lib as _lib
+    cov4 = torch.empty((D, D), device=dev)
+    xty4 = torch.empty((D, D), device=dev)
+    r4d = torch.from_numpy(np.ascontiguousarray(r4)).to(dev)
+    cen4 = torch.from_numpy(q).to(dev).clone()
+    st_raw = stream.cuda_stream
+    opq = {}
+    for name, call in (("covariance_ms", lambda: _check(_lib.rb_covariance(x4.data_ptr(), n4, D, x4.stride(0), cov4.data_ptr(), st_raw))),
+                       ("train_iteration_ms", lambda: _check(_lib.rb_opq_train_iteration(
+                           x4.data_ptr(), n4, D, x4.stride(0), r4d.data_ptr(), cen4.data_ptr(), M, K_CENTROIDS, xty4.data_ptr(), st_raw)))):
+        call()
+        barrier()
+        k0.record(stream)
+        for _ in range(3):
+            call()
+        k1.record(stream)
+        barrier()
+        opq[name] = k0.elapsed_time(k1) / 3
+    extra["opq_training"] = {"workload": "1M x 300 per GPU, M = 30, k = 256: rb_covariance (column means + centred Gram on tcgen05) and "
+                                         "rb_opq_train_iteration (exact-order X.R, k-means step, encode, gather, X^T.Y^ on tcgen05)",
+                             **opq, "covariance_tflops": 2 * n4 * D * D / (opq["covariance_ms"] * 1e-3) / 1e12}
+    del cov4, xty4
+    log("OPQ training legs done")
     # the caller-side quantized storage over the C2 codes (2M x 30 u8 + norms resident in HBM):
     # fused decode + dot of 8 / 64 queries against every stored row (rb_qstore_dot)
     store = rb.QuantizedArray(pq, codes, torch.rand((N_ROWS,), device=dev) + 0.5)
