@@ -699,39 +699,44 @@ namespace {
 
 // sum over rows of ||x_m||^2 per subquantizer in FP64 with a FIXED summation order (fixed row ranges per block, fixed
 // strides per thread, tree reduction, partials added in block order): run-to-run identical, unlike float atomics.
-constexpr int kSqBlocks = 64;
-
+// sum ||x_m||^2 over all rows per subquantizer, in FP64 with a fixed order (the losses that rank training attempts must
+// not depend on the run): a thread owns one column of a row split (coalesced row reads, eight in flight), then one
+// warp per subquantizer adds the splits and the subquantizer's columns in a fixed pattern.
 __global__ void __launch_bounds__(256)
-sumsq_partial_kernel(const float *__restrict__ x, long long n, long long ldx, int dsub, double *__restrict__ partial)
+sumsq_partial_kernel(const float *__restrict__ x, long long n, long long ldx, int d, long long rows_per_split,
+                     double *__restrict__ partial)
 {
-    const int m = blockIdx.y;
-    const long long per = (n + kSqBlocks - 1) / kSqBlocks;
-    const long long r0 = (long long)blockIdx.x * per, r1 = min(n, r0 + per);
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(n, r0 + rows_per_split);
+    if (col >= d) return;
     double acc = 0.0;
-    const long long total = (r1 > r0 ? r1 - r0 : 0) * dsub;
-    for (long long i = threadIdx.x; i < total; i += 256) {
-        const long long r = r0 + i / dsub;
-        const int t = (int)(i % dsub);
-        const float v = __ldg(x + r * ldx + (long long)m * dsub + t);
+    long long r = r0;
+    for (; r + 8 <= r1; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = __ldg(x + (r + e) * ldx + col);
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc += (double)v[e] * (double)v[e];
+    }
+    for (; r < r1; r++) {
+        const float v = __ldg(x + r * ldx + col);
         acc += (double)v * (double)v;
     }
-    __shared__ double red[256];
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) partial[(size_t)m * kSqBlocks + blockIdx.x] = red[0];
+    partial[(size_t)blockIdx.y * d + col] = acc;
 }
 
-__global__ void sumsq_final_kernel(const double *__restrict__ partial, int M, double *__restrict__ out)
+__global__ void __launch_bounds__(256)
+sumsq_final_kernel(const double *__restrict__ partial, int M, int dsub, int n_splits, double *__restrict__ out)
 {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (m >= M) return;
+    const int d = M * dsub;
     double s = 0.0;
-    for (int b = 0; b < kSqBlocks; b++) s += partial[(size_t)m * kSqBlocks + b];
-    out[m] = s;
+    for (int p = lane; p < n_splits; p += 32)
+        for (int t = 0; t < dsub; t++) s += partial[(size_t)p * d + (size_t)m * dsub + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[m] = s;
 }
 
 }  // namespace
@@ -739,10 +744,15 @@ __global__ void sumsq_final_kernel(const double *__restrict__ partial, int M, do
 rb_status launch_sumsq64(const float *x, size_t n, ptrdiff_t ldx, size_t M, size_t dsub, double *out, cudaStream_t stream)
 {
     if (M == 0) return RB_OK;
+    const size_t d = M * dsub;
+    size_t rows_per_split = 512;
+    if (ceil_div(n ? n : 1, rows_per_split) > 4096) rows_per_split = ceil_div(n, (size_t)4096);
+    const size_t splits = n ? ceil_div(n, rows_per_split) : 1;
     double *partial = nullptr;
-    RB_CUDA_TRY(pool_malloc((void **)&partial, M * kSqBlocks * sizeof(double), stream));
-    sumsq_partial_kernel<<<dim3(kSqBlocks, (unsigned)M), 256, 0, stream>>>(x, (long long)n, (long long)ldx, (int)dsub, partial);
-    sumsq_final_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, stream>>>(partial, (int)M, out);
+    RB_CUDA_TRY(pool_malloc((void **)&partial, splits * d * sizeof(double), stream));
+    sumsq_partial_kernel<<<dim3((unsigned)ceil_div(d, (size_t)256), (unsigned)splits), 256, 0, stream>>>(
+        x, (long long)n, (long long)ldx, (int)d, (long long)rows_per_split, partial);
+    sumsq_final_kernel<<<(unsigned)ceil_div(M, (size_t)8), 256, 0, stream>>>(partial, (int)M, (int)dsub, (int)splits, out);
     cudaFreeAsync(partial, stream);
     RB_LAUNCH_CHECK();
     return RB_OK;

@@ -590,6 +590,24 @@ def test_tensor_margin_holds_across_scales_and_widths(oracle, dsub, scale):
     assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ"
 
 
+@pytest.mark.parametrize("dsub", [8, 10])
+@pytest.mark.parametrize("spread", [(1.0, 1e3, 1e-3, 1.0), (1e4, 1.0, 1e-4, 3e2)])
+def test_tensor_margin_with_wide_subquantizer_scale_spread(oracle, dsub, spread):
+    """with ONE operand scale for all subquantizers, a subquantizer 1e3-1e4x smaller than the largest fell
+    into FP16 subnormals and the certificate could certify a wrong winner.  The scale is per subquantizer now; near-tie
+    rows in every subquantizer of codebooks with 1e3x and 1e8x spreads must come out bit-exact."""
+    M, k = 4, 256
+    q = random_codebook(M, k, dsub, 5000 + dsub)
+    q = (q * np.array(spread, F)[:, None, None]).astype(F)
+    rows = near_tie_rows(q, 8_000, 6000 + dsub)
+    rnd = normal((3_000, M * dsub), 7000 + dsub) * np.repeat(np.array(spread, F), dsub)[None, :]
+    x = np.concatenate([rows, rnd.astype(F)]).astype(F)
+    rb.set_encode_algo(rb.ENCODE_AUTO)
+    codes = rb.Pq(None, q).quantize_batch(x, np.uint8)
+    want = oracle.quantize_batch(q, None, x, np.uint8, n_threads=8)
+    assert np.array_equal(codes, want), f"{(codes != want).sum()} codes differ"
+
+
 def test_pageable_and_pinned_host_buffers_give_the_same_codes(oracle, torch_cuda):
     """The host-memory pipeline stages pageable memory through pinned buffers of its own (several chunks, both
     slots, strided rows); pinned memory is copied from directly."""
