@@ -186,3 +186,19 @@ def test_nccl_is_resolved_to_the_copy_torch_uses():
     env = {k: v for k, v in os.environ.items() if k != "RB_NCCL_LIB"}
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_new_entry_points_validate_their_arguments_without_a_device():
+    """Argument errors are reported before any device work (no GPU needed)."""
+    import ctypes as C
+
+    from reductive_b200._cabi import lib
+
+    assert lib.rb_set_gram_algo(7) != 0 and lib.rb_set_gram_algo(0) == 0
+    h = C.c_void_p()
+    assert lib.rb_qstore_create(None, None, 0, 0, None, 0, None, C.byref(h)) != 0 and not h.value
+    assert lib.rb_qstore_len(None) == 0 and lib.rb_qstore_has_norms(None) == 0
+    assert lib.rb_qstore_dot(None, None, 1, 1, 1, None, 1, 0, None) != 0
+    assert lib.rb_qstore_embeddings(None, None, 1, None, 1, 1, 0, None) != 0
+    assert lib.rb_kmeans_dist_peer_window(None) == 0
+    lib.rb_qstore_destroy(None)  # no-op
