@@ -264,7 +264,7 @@ rb_status rb_qstore_embeddings(const rb_qstore *store, const uint64_t *indices, 
                                ptrdiff_t out_row_stride, ptrdiff_t out_col_stride, int mem_kind, void *stream);
 /* Fused decode + dot: out[q, i] = queries[q, :] . embedding(i) for every stored row, without materialising the
  * [n, d] reconstruction: per query one table of subvector-centroid dot products (the query is rotated by the
- * projection first, q . (y R^T) = (q R) . y), then one pass over the codes per batch of up to 8 queries.  f32
+ * projection first, q . (y R^T) = (q R) . y), then one pass over the codes per batch of up to 8 queries (as many as fit their lookup table in shared memory: 4 at M = 30, k = 256).  f32
  * accumulation, subquantizers in ascending order: within 1e-5 * sum_c |q_c| |e_c| of the exact product.
  * queries: [nq, d] with element strides; out: [nq, len] with row stride out_row_stride; both in mem_kind memory.
  * DEVICE calls are asynchronous on `stream`. */
