@@ -248,20 +248,25 @@ rb_status launch_gram_tensor(const float *a, ptrdiff_t lda, const float *b, ptrd
     const size_t n_blocks = ceil_div(npad, (size_t)kGmMaxBlock);
     const size_t nw = ceil_div(ceil_div(npad, n_blocks), (size_t)16) * 16;
     const size_t dpad_a = m_tiles * 128, dpad_b = n_blocks * nw;
-    const size_t steps = ceil_div(n, (size_t)16), groups = 2 * steps;
     const bool same = a == b && lda == ldb && da == db && a_sub == b_sub;
     const size_t dpad_same = dpad_a > dpad_b ? dpad_a : dpad_b;
+    const int dpa = (int)(same ? dpad_same : dpad_a);
+
+    // The rows go through in passes of at most pass_rows (the limb arrays of a pass: 32 bytes per element, i.e. 8 GB
+    // for 4 M rows x 512 columns and operand); every pass fills its own slots of the partial buffer and the final
+    // kernel adds all of them in order.  RB_GRAM_PASS_ROWS: development aid (tests force several passes).
+    const char *pass_env = getenv("RB_GRAM_PASS_ROWS");
+    const long long pass_req = pass_env ? atoll(pass_env) : 0;
+    const size_t pass_rows = pass_req >= 4096 ? (size_t)pass_req / 16 * 16 : (size_t)4 << 20;
+    const size_t n_pass = ceil_div(n, pass_rows);
+    const size_t steps_full = ceil_div(n < pass_rows ? n : pass_rows, (size_t)16);
+    size_t splits_max = (size_t)sm_count() / (m_tiles * n_blocks);
+    if (splits_max < 1) splits_max = 1;
 
     GramMmaParams p;
     p.da = (int)da;
     p.db = (int)db;
     p.nw = (int)nw;
-    p.steps = (long long)steps;
-    size_t splits = (size_t)sm_count() / (m_tiles * n_blocks);
-    if (splits < 1) splits = 1;
-    if (splits > ceil_div(steps, (size_t)64)) splits = ceil_div(steps, (size_t)64);
-    p.steps_per_split = (long long)ceil_div(steps, splits);
-    splits = ceil_div(steps, (size_t)p.steps_per_split);
     const size_t stage_bytes = 2 * (2 * 128 * 16) + 2 * (2 * nw * 16);
     const size_t tile_bytes = nw * 128 * sizeof(float);
     p.stages = (int)std::min<size_t>(8, (226 * 1024 - tile_bytes - 256) / stage_bytes);
@@ -273,36 +278,48 @@ rb_status launch_gram_tensor(const float *a, ptrdiff_t lda, const float *b, ptrd
 
     uint4 *limbs = nullptr;
     float *partial = nullptr;
-    const size_t a_vecs = groups * (same ? dpad_same : dpad_a), b_vecs = same ? 0 : groups * dpad_b;
+    const size_t groups_full = 2 * steps_full;
+    const size_t a_vecs = groups_full * (size_t)dpa, b_vecs = same ? 0 : groups_full * dpad_b;
     RB_CUDA_TRY(pool_malloc((void **)&limbs, 2 * (a_vecs + b_vecs) * sizeof(uint4), stream));
     rb_status st = [&]() -> rb_status {
-        RB_CUDA_TRY(pool_malloc((void **)&partial, splits * da * db * sizeof(float), stream));
-        uint4 *a_hi = limbs, *a_lo = limbs + a_vecs, *b_hi = limbs + 2 * a_vecs, *b_lo = limbs + 2 * a_vecs + b_vecs;
-        const int dpa = (int)(same ? dpad_same : dpad_a);
-        const unsigned gy = (unsigned)std::min<size_t>(ceil_div(groups, (size_t)4), (size_t)sm_count() * 16);
-        gram_limbs_kernel<<<dim3((unsigned)ceil_div((size_t)dpa, (size_t)128), gy), 128, 0, stream>>>(
-            a, (long long)n, (long long)lda, (int)da, dpa, (long long)groups, a_sub, a_hi, a_lo);
-        RB_LAUNCH_CHECK();
-        if (same) {
-            b_hi = a_hi;
-            b_lo = a_lo;
-            p.dpad_a = p.dpad_b = dpa;
-        } else {
-            gram_limbs_kernel<<<dim3((unsigned)ceil_div(dpad_b, (size_t)128), gy), 128, 0, stream>>>(
-                b, (long long)n, (long long)ldb, (int)db, (int)dpad_b, (long long)groups, b_sub, b_hi, b_lo);
-            RB_LAUNCH_CHECK();
-            p.dpad_a = (int)dpad_a;
-            p.dpad_b = (int)dpad_b;
-        }
-        p.a_hi = a_hi;
-        p.a_lo = a_lo;
-        p.b_hi = b_hi;
-        p.b_lo = b_lo;
-        p.partial = partial;
+        RB_CUDA_TRY(pool_malloc((void **)&partial, n_pass * splits_max * da * db * sizeof(float), stream));
         RB_CUDA_TRY(cudaFuncSetAttribute(gram_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gram_mma_kernel<<<dim3((unsigned)m_tiles, (unsigned)n_blocks, (unsigned)splits), kGmThreads, smem, stream>>>(p);
-        RB_LAUNCH_CHECK();
-        gram_tc_final_kernel<<<(unsigned)ceil_div(da * db, (size_t)256), 256, 0, stream>>>(partial, (int)da, (int)db, (int)splits,
+        uint4 *a_hi = limbs, *a_lo = limbs + a_vecs, *b_hi = limbs + 2 * a_vecs, *b_lo = limbs + 2 * a_vecs + b_vecs;
+        size_t slots = 0;  // partial tiles written so far
+        for (size_t ps = 0; ps < n_pass; ps++) {
+            const size_t r0 = ps * pass_rows, rows = n - r0 < pass_rows ? n - r0 : pass_rows;
+            const size_t steps = ceil_div(rows, (size_t)16), groups = 2 * steps;
+            const unsigned gy = (unsigned)std::min<size_t>(ceil_div(groups, (size_t)4), (size_t)sm_count() * 16);
+            gram_limbs_kernel<<<dim3((unsigned)ceil_div((size_t)dpa, (size_t)128), gy), 128, 0, stream>>>(
+                a + (ptrdiff_t)r0 * lda, (long long)rows, (long long)lda, (int)da, dpa, (long long)groups, a_sub, a_hi, a_lo);
+            RB_LAUNCH_CHECK();
+            if (same) {
+                p.b_hi = a_hi;
+                p.b_lo = a_lo;
+                p.dpad_a = p.dpad_b = dpa;
+            } else {
+                gram_limbs_kernel<<<dim3((unsigned)ceil_div(dpad_b, (size_t)128), gy), 128, 0, stream>>>(
+                    b + (ptrdiff_t)r0 * ldb, (long long)rows, (long long)ldb, (int)db, (int)dpad_b, (long long)groups, b_sub, b_hi,
+                    b_lo);
+                RB_LAUNCH_CHECK();
+                p.b_hi = b_hi;
+                p.b_lo = b_lo;
+                p.dpad_a = (int)dpad_a;
+                p.dpad_b = (int)dpad_b;
+            }
+            p.a_hi = a_hi;
+            p.a_lo = a_lo;
+            p.steps = (long long)steps;
+            size_t splits = splits_max;
+            if (splits > ceil_div(steps, (size_t)64)) splits = ceil_div(steps, (size_t)64);
+            p.steps_per_split = (long long)ceil_div(steps, splits);
+            splits = ceil_div(steps, (size_t)p.steps_per_split);
+            p.partial = partial + slots * da * db;
+            gram_mma_kernel<<<dim3((unsigned)m_tiles, (unsigned)n_blocks, (unsigned)splits), kGmThreads, smem, stream>>>(p);
+            RB_LAUNCH_CHECK();
+            slots += splits;
+        }
+        gram_tc_final_kernel<<<(unsigned)ceil_div(da * db, (size_t)256), 256, 0, stream>>>(partial, (int)da, (int)db, (int)slots,
                                                                                            b_div, out);
         RB_LAUNCH_CHECK();
         return RB_OK;

@@ -680,6 +680,27 @@ def test_tensor_core_gram_matches_float64(torch_cuda, n, d, pad):
     assert np.abs(got_tc - got_tc.T).max() <= 4e-6 * scale
 
 
+def test_tensor_core_gram_in_several_row_passes(torch_cuda, monkeypatch):
+    """Large inputs go through gram_tc.cu in row passes that share one partial buffer (RB_GRAM_PASS_ROWS forces the
+    passes small here): the same tolerance, and the ragged last pass counts."""
+    torch = torch_cuda
+    from reductive_b200._cabi import GRAM_AUTO, GRAM_TENSOR, check, lib, set_gram_algo
+
+    n, d = 21_003, 200
+    a = (normal((n, d), 123) * np.linspace(0.5, 2, d, dtype=F) + F(0.3)).astype(F)
+    ad = torch.from_numpy(a).cuda()
+    c = a.astype(np.float64) - a.mean(0, dtype=np.float64)
+    want = c.T @ c / (n - 1)
+    monkeypatch.setenv("RB_GRAM_PASS_ROWS", "8192")
+    set_gram_algo(GRAM_TENSOR)
+    try:
+        out = torch.empty((d, d), device="cuda")
+        check(lib.rb_covariance(ad.data_ptr(), n, d, ad.stride(0), out.data_ptr(), None))
+    finally:
+        set_gram_algo(GRAM_AUTO)
+    assert np.abs(out.cpu().numpy() - want).max() <= 1e-5 * np.abs(want).max()
+
+
 @pytest.mark.parametrize("n,M,k,dsub", [(6_000, 4, 16, 6), (20_000, 8, 256, 8)])
 def test_opq_train_iteration_matches_the_oracle(oracle, torch_cuda, n, M, k, dsub):
     """Opq::train_iteration (opq.rs:161-189) from identical projection and centroids: the k-means step is bit-identical
