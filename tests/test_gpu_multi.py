@@ -14,7 +14,8 @@ def _devices():
     return list(range(torch.cuda.device_count()))
 
 
-@pytest.mark.parametrize("n,M,bits,dsub,iters", [(20_000, 8, 8, 8, 6), (5_003, 6, 6, 10, 4), (3_000, 5, 4, 4, 3)])
+@pytest.mark.parametrize("n,M,bits,dsub,iters", [(20_000, 8, 8, 8, 6), (5_003, 6, 6, 10, 4), (3_000, 5, 4, 4, 3),
+                                                (6_001, 4, 9, 4, 3)])  # bits = 9: 4-byte codes through the exchange
 def test_multi_gpu_training_is_bit_identical_to_one_gpu(oracle, n, M, bits, dsub, iters):
     import reductive_b200 as rb
 
