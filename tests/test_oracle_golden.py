@@ -151,3 +151,72 @@ def test_quantize_with_pq_statistical(oracle):
     rec = oracle.reconstruct_batch(q, None, codes)
     loss = np.mean(np.sqrt(((x - rec) ** 2).sum(1)))
     assert loss < 0.08
+
+
+# ---- OPQ-training restatement (oracle.py: covariance / create_projection_matrix / opq_train_iteration) ----------
+def test_covariance_known_answer(oracle):  # linalg.rs:253-261
+    x = np.array([[0., 2.], [1., 1.], [2., 0.]], F)
+    assert np.array_equal(oracle.covariance(x), np.array([[1., -1.], [-1., 1.]], F))
+    # the transposed view with the other axis (linalg.rs:259-260) is the same computation on x
+    assert np.array_equal(oracle.covariance(np.ascontiguousarray(x.T).T), np.array([[1., -1.], [-1., 1.]], F))
+
+
+def test_covariance_agrees_with_float64(oracle):
+    rng = np.random.default_rng(3)
+    x = (rng.normal(size=(4_000, 24)) * np.linspace(0.5, 3, 24) + np.linspace(-1, 1, 24)).astype(F)
+    c = x.astype(np.float64) - x.mean(0, dtype=np.float64)
+    want = c.T @ c / (len(x) - 1)
+    got = oracle.covariance(x)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_projection_matrix_is_an_eigenbasis_permutation(oracle):  # opq.rs:103-136
+    """create_projection_matrix: the eigenvectors of the covariance, columns permuted by the eigenvalue bucketing
+    (opq.rs:212-273): orthonormal, and it diagonalises the covariance."""
+    rng = np.random.default_rng(5)
+    x = (rng.normal(size=(3_000, 12)) @ rng.normal(size=(12, 12))).astype(F)
+    p = oracle.create_projection_matrix(x, 4)
+    assert p.shape == (12, 12) and p.dtype == F
+    assert np.abs(p.T @ p - np.eye(12)).max() < 1e-5
+    rot = p.astype(np.float64).T @ oracle.covariance(x).astype(np.float64) @ p.astype(np.float64)
+    off = rot - np.diag(np.diag(rot))
+    assert np.abs(off).max() < 1e-4 * np.abs(np.diag(rot)).max()
+    # buckets of 3 consecutive columns: their eigenvalue products are balanced (what bucket_eigenvalues optimises)
+    logs = np.log(np.diag(rot)).reshape(4, 3).sum(1)
+    assert logs.max() - logs.min() < np.log(np.diag(rot)).max() - np.log(np.diag(rot)).min()
+
+
+def test_opq_train_iteration_is_a_rotation_and_does_not_increase_the_error(oracle):  # opq.rs:161-189
+    rng = np.random.default_rng(7)
+    M, k, dsub, n = 3, 8, 2, 1_500
+    x = (rng.normal(size=(n, M * dsub)) @ rng.normal(size=(M * dsub, M * dsub))).astype(F)
+    r = oracle.create_projection_matrix(x, M)
+    rx = oracle.sgemm(x, r)
+    c = np.stack([rx[rng.choice(n, k, replace=False)][:, m * dsub:(m + 1) * dsub] for m in range(M)])
+
+    def err(r_, c_):
+        rx_ = oracle.sgemm(x, r_)
+        rec = oracle.reconstruct_batch(c_, None, oracle.quantize_batch(c_, None, rx_, np.uint32))
+        return float(((rx_ - rec) ** 2).sum())
+
+    e0 = err(r, c)
+    for _ in range(3):
+        r, c, xty = oracle.opq_train_iteration(r, c, x)
+        assert np.abs(r.T @ r - np.eye(M * dsub)).max() < 1e-4 and xty.shape == (M * dsub, M * dsub)
+    assert err(r, c) <= e0 * 1.0001
+
+
+def test_qstore_restatement_is_reconstruct_times_norm(oracle):
+    """The storage layer's oracle (parity unpinned: outside the reference tree) is reconstruct_batch x norm, and its
+    exact scores are the float64 products of those embeddings."""
+    rng = np.random.default_rng(9)
+    q = rng.normal(size=(3, 16, 4)).astype(F)
+    codes = rng.integers(0, 16, (50, 3)).astype(np.uint8)
+    norms = rng.uniform(0.5, 2, 50).astype(F)
+    idx = np.array([0, 49, 7, 7])
+    e = oracle.qstore_embeddings(q, None, codes, norms, idx)
+    assert np.array_equal(e, oracle.reconstruct_batch(q, None, codes[idx]) * norms[idx][:, None])
+    queries = rng.normal(size=(2, 12)).astype(F)
+    s, mag = oracle.qstore_dot(q, None, codes, norms, queries)
+    full = oracle.qstore_embeddings(q, None, codes, norms, np.arange(50)).astype(np.float64)
+    assert np.allclose(s, queries.astype(np.float64) @ full.T) and np.all(mag >= np.abs(s) - 1e-12)
