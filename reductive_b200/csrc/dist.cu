@@ -309,7 +309,20 @@ rb_status window_setup(rb_kmeans_dist *h, cudaStream_t st)
     prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     prop.location.id = h->c->device;
     prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
-    int my_fd = -1, sock = -1;
+    struct Fd {  // closed on every way out, also when a collective fails
+        int v = -1;
+        ~Fd()
+        {
+            if (v >= 0) close(v);
+        }
+        Fd &operator=(int x)
+        {
+            v = x;
+            return *this;
+        }
+        operator int() const { return v; }
+        int *ptr() { return &v; }
+    } my_fd, sock;
     if (ok) {
         size_t g = 0;
         ok = d.MemGranularity(&g, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) == CUDA_SUCCESS && g != 0 && kWindowGranule % g == 0;
@@ -317,7 +330,7 @@ rb_status window_setup(rb_kmeans_dist *h, cudaStream_t st)
     if (ok && m_own) {
         ok = d.MemCreate(&w.handle[me], m_own * w.pitch, &prop, 0) == CUDA_SUCCESS;
         if (!ok) w.handle[me] = 0;
-        if (ok) ok = d.MemExport(&my_fd, w.handle[me], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+        if (ok) ok = d.MemExport(my_fd.ptr(), w.handle[me], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
     }
     // a socket name nobody else uses: rank 0's random token
     unsigned long long token = 0;
@@ -382,8 +395,6 @@ rb_status window_setup(rb_kmeans_dist *h, cudaStream_t st)
         if (ok && m_own)
             ok = cudaMemsetAsync(reinterpret_cast<void *>(w.va + h->m_lo[me] * w.pitch), 0, m_own * w.pitch, st) == cudaSuccess;
     }
-    if (my_fd >= 0) close(my_fd);
-    if (sock >= 0) close(sock);
     RB_TRY(exchange_u64(h, st, (go && ok) ? 1ull : 0ull, all));
     bool active = true;
     for (int r = 0; r < W; r++) active = active && all[r] != 0;
