@@ -32,7 +32,8 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 2
+/* 3: + rb_qstore_*, rb_set_gram_algo, rb_kmeans_dist_peer_window (additions only; version-2 callers keep working) */
+#define RB_ABI_VERSION 3
 
 /* Status codes.  1..6 mirror ReductiveError (src/error.rs:6-41); 16.. are the reference's panics
  * (assert sites: primitives.rs:25-34,74-87,123-135,159-167; pq.rs:39-55; kmeans.rs:61-71,269-277),

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_cabi.EXPORTED_SYMBOLS) == declared
     for name in declared:
         assert hasattr(_cabi.lib, name), f"{name} is declared in include/reductive_b200.h but not exported"
-    assert _cabi.lib.rb_abi_version() == 2
+    assert _cabi.lib.rb_abi_version() == 3
 
 
 def test_check_quantizer_invariants_matches_oracle(oracle):
